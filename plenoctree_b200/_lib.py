@@ -1,0 +1,71 @@
+"""ctypes binding of libplenoctree_b200.so (the C ABI in include/plenoctree_b200.h).
+
+There is no fallback: if the shared library is missing the import raises, and every compute entry
+point fails when no sm_100 device is present.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplenoctree_b200.so")
+
+PREC_FP16 = 1
+PREC_FP16X3 = 3
+
+_c = ctypes
+_vp, _i, _i64, _u32, _fp = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint32, _c.c_void_p
+
+# name -> (restype, argtypes); must list every symbol the header declares
+SIGNATURES = {
+    "pob_abi_version": (_i, []),
+    "pob_last_error": (_c.c_char_p, []),
+    "pob_sm_count": (_i, []),
+    "pob_param_count": (_i64, [_i]),
+    "pob_packed_bytes": (_i64, [_i]),
+    "pob_pack_weights": (_i, [_fp, _i, _vp, _vp]),
+    "pob_eval_points_raw": (_i, [_vp, _i, _fp, _i64, _fp, _fp, _i, _vp]),
+    "pob_eval_points": (_i, [_vp, _i, _fp, _fp, _i64, _fp, _i, _vp]),
+    "pob_eval_grid": (_i, [_vp, _i, _i, _i, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
+                           _fp, _fp, _i, _vp]),
+    "pob_eval_points_raw_host": (_i, [_vp, _i, _fp, _i64, _fp, _fp, _i]),
+    "pob_umma_probe": (_i, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i, _u32, _i, _fp, _vp]),
+}
+
+
+class PobError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m plenoctree_b200.build` "
+            "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise PobError(lib.pob_last_error().decode())
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

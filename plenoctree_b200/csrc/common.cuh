@@ -1,0 +1,315 @@
+// common.cuh — sm_100a building blocks shared by every kernel of the NeRF-SH hot path.
+//
+// Everything here is a thin inline-PTX wrapper (mbarrier, bulk async copy = TMA 1-D,
+// tcgen05 alloc / mma / commit / ld, proxy fences) plus the shared-memory operand
+// layouts the tensor-core kernels agree on.  No CUTLASS / CuTe types: the descriptor
+// bit layouts were checked against cute/arch/mma_sm100_desc.hpp (SmemDescriptor,
+// InstrDescriptor) and cute/atom/mma_traits_sm100.hpp (canonical K-/MN-major layouts).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace pob {
+
+// ----------------------------------------------------------------------------------
+// Geometry shared by all MLP kernels
+// ----------------------------------------------------------------------------------
+constexpr int TILE_M      = 128;           // samples (rows) per tensor-core tile
+constexpr int WIDTH       = 256;           // trunk width (reference net_width)
+constexpr int ENC_DIM     = 63;            // posenc(x, 0, 10) feature count
+constexpr int ENC_PAD     = 64;            // padded to one 64-wide K chunk
+constexpr int NUM_TRUNK   = 8;             // net_depth
+constexpr int SKIP_LAYER  = 5;             // layer that consumes [h4, enc] (skip after i=4)
+constexpr int KCHUNK      = 64;            // fp16 elements per 128-byte swizzle row
+constexpr int A_CHUNK_BYTES = TILE_M * 128;        // one [128 x 64] fp16 K-chunk, SW128
+constexpr int A_TILE_BYTES  = 4 * A_CHUNK_BYTES;   // [128 x 256] fp16 = 64 KB
+constexpr int E_TILE_BYTES  = A_CHUNK_BYTES;       // [128 x 64]  fp16 = 16 KB
+constexpr int WSLOT_K       = 32;                  // K extent of one streamed weight slot
+constexpr int WSLOT_BYTES   = WIDTH * WSLOT_K * 2; // [256 x 32] fp16, SW64 = 16 KB
+constexpr int NUM_WSLOTS    = 4;                   // weight ring depth
+constexpr int MAX_NH        = 80;                  // padded heads width (1 + 3*25 -> 80)
+
+// number of 32-wide K slots each forward layer streams (trunk 0..7, heads = index 8)
+__host__ __device__ constexpr int fwd_slots_of_layer(int l) {
+  return l == 0 ? 2 : (l == SKIP_LAYER ? 10 : 8);
+}
+constexpr int FWD_SLOTS_TOTAL = 2 + 8 * 4 + 10 + 8 * 2 + 8;  // 68 per MLP pass
+
+// ----------------------------------------------------------------------------------
+// Small helpers
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ----------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// Proxy / tcgen05 fences
+// ----------------------------------------------------------------------------------
+// generic-proxy st.shared -> visible to the async proxy (UMMA operand reads, bulk stores)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// Bulk async copies (TMA, 1-D).  SASS: UBLKCP.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until the smem source of all committed bulk stores has been read
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// Named barriers (sub-CTA sync)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// TMEM allocation (one full warp executes these)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// UMMA (tcgen05.mma) — fp16 x fp16 -> fp32, operands from shared memory.  SASS: UTCHMMA.
+// ----------------------------------------------------------------------------------
+// Instruction descriptor (cute::UMMA::InstrDescriptor):
+//   [4,6) c_format (1 = F32) | [7,10) a_format (0 = F16) | [10,13) b_format (0 = F16)
+//   [15] a_major (0 = K, 1 = MN) | [16] b_major | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major = 0,
+                                                      int b_mn_major = 0) {
+  return (1u << 4) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version = 1 | [61,64) layout type
+enum : uint32_t { LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6, LAYOUT_NONE = 0 };
+__host__ __device__ constexpr uint64_t make_sdesc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(layout) << 61);
+}
+__host__ __device__ constexpr uint64_t make_sdesc(uint32_t addr, uint32_t lbo_bytes,
+                                                  uint32_t sbo_bytes, uint32_t layout) {
+  return uint64_t((addr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         make_sdesc_hi(sbo_bytes, layout);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// TMEM -> registers.  32x32b: thread i of the warp reads lane (32*(warp%4)+i), N consecutive
+// 32-bit columns.  SASS: LDTM.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// fp32 pair -> packed fp16x2 (element `lo` at the lower address), optional fused ReLU
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+
+// ----------------------------------------------------------------------------------
+// Operand layouts
+// ----------------------------------------------------------------------------------
+// Activation tile ("A image"): [nchunk][128 rows][128 B], each row = 64 fp16 of one sample,
+// 16-byte units XOR-swizzled with (row & 7)  (= cute Swizzle<3,4,3>, K-major SW128 atom).
+// The same bytes are a valid MN-major SW128 operand of the transposed matrix (features x
+// samples): LBO = chunk stride, SBO = 1024 (8 samples).
+__host__ __device__ __forceinline__ constexpr uint32_t a_tile_offset(int row, int col) {
+  // byte offset of element (row, col) of a [128 x 64*nchunk] tile
+  return uint32_t(col >> 6) * A_CHUNK_BYTES + uint32_t(row) * 128u +
+         ((uint32_t((col >> 3) & 7) ^ uint32_t(row & 7)) << 4) + uint32_t(col & 7) * 2u;
+}
+// Weight slot ("W image"): [rows][64 B] = 32 fp16 (K) per output row, 16-byte units
+// XOR-swizzled with ((row >> 1) & 3)  (= cute Swizzle<2,4,3>, K-major SW64 atom).
+__host__ __device__ __forceinline__ constexpr uint32_t w_slot_offset(int row, int k) {
+  return uint32_t(row) * 64u + ((uint32_t((k >> 3) & 3) ^ (uint32_t(row >> 1) & 3u)) << 4) +
+         uint32_t(k & 7) * 2u;
+}
+
+// accurate-enough sine for the positional encoding: Cody-Waite reduction by 2*pi followed by
+// the SFU approximation (abs err ~5e-7 for |x| < 1e4); PRECISE selects libdevice sinf.
+template <bool PRECISE>
+__device__ __forceinline__ float posenc_sin(float a) {
+  if (PRECISE) {
+    return sinf(a);
+  } else {
+    float k = rintf(a * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, a);
+    r = fmaf(k, 1.7484555314695172e-7f, r);
+    return __sinf(r);
+  }
+}
+
+// Real SH basis, sign/ordering convention of the reference (nerf_sh/nerf/sh.py:54-109).
+// basis[k] for k < (deg+1)^2; entries beyond are untouched.
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float (&b)[25]) {
+  b[0] = 0.28209479177387814f;
+  if (deg > 0) {
+    b[1] = -0.4886025119029199f * y;
+    b[2] = 0.4886025119029199f * z;
+    b[3] = -0.4886025119029199f * x;
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      b[4] = 1.0925484305920792f * xy;
+      b[5] = -1.0925484305920792f * yz;
+      b[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+      b[7] = -1.0925484305920792f * xz;
+      b[8] = 0.5462742152960396f * (xx - yy);
+      if (deg > 2) {
+        b[9] = -0.5900435899266435f * y * (3.f * xx - yy);
+        b[10] = 2.890611442640554f * xy * z;
+        b[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+        b[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        b[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+        b[14] = 1.445305721320277f * z * (xx - yy);
+        b[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+        if (deg > 3) {
+          b[16] = 2.5033429417967046f * xy * (xx - yy);
+          b[17] = -1.7701307697799304f * yz * (3.f * xx - yy);
+          b[18] = 0.9461746957575601f * xy * (7.f * zz - 1.f);
+          b[19] = -0.6690465435572892f * yz * (7.f * zz - 3.f);
+          b[20] = 0.10578554691520431f * (zz * (35.f * zz - 30.f) + 3.f);
+          b[21] = -0.6690465435572892f * xz * (7.f * zz - 3.f);
+          b[22] = 0.47308734787878004f * (xx - yy) * (7.f * zz - 1.f);
+          b[23] = -1.7701307697799304f * xz * (xx - 3.f * yy);
+          b[24] = 0.6258357354491761f * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+        }
+      }
+    }
+  }
+}
+
+}  // namespace pob

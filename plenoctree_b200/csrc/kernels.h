@@ -1,0 +1,94 @@
+// kernels.h — internal launch interface between the C-ABI (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pob {
+
+// ---- packed weights of one MLP (device pointers; produced by launch_pack_weights) ----------
+struct MlpPacked {
+  const uint8_t* w_hi;    // forward slot images, fp16 "hi" part  (fwd_image_bytes(NH))
+  const uint8_t* w_lo;    // forward slot images, fp16 residual   (same layout)
+  const uint8_t* wt_hi;   // dgrad slot images (transposed weights), fp16
+  const float* bias;      // [8*256 + MAX_NH]: trunk biases then heads bias in packed order
+};
+
+enum SrcMode : int { SRC_POINTS = 0, SRC_RAYS = 1, SRC_GRID = 2 };
+enum OutMode : int { OUT_RAW = 0, OUT_SIGMA = 1, OUT_RGBS = 2 };
+
+struct FwdParams {
+  // ---- sample source ----
+  int src_mode;
+  long long M;                 // number of samples (rows)
+  const float* points;         // SRC_POINTS: [M,3]
+  const float* origins;        // SRC_RAYS:   [R,3]
+  const float* directions;     //             [R,3]
+  const float* zvals;          //             [R, n_per_ray]
+  int n_per_ray;
+  const float* viewdirs;       // OUT_RGBS: [R,3] (SRC_RAYS) or [M,3] (SRC_POINTS)
+  // SRC_GRID: voxel centres ((i + 0.5)/reso - offset)/scale, x-major flattening (ix,iy,iz)
+  int g_reso;                  // arange length the reference normalises by
+  int g_x0, g_nx, g_ny, g_nz;  // slab: ix in [g_x0, g_x0+g_nx), iy in [0,g_ny), iz in [0,g_nz)
+  float g_offset[3], g_scale[3];
+  // ---- model ----
+  MlpPacked w;
+  int sh_deg;                  // -1: 3 raw rgb channels, K = 1
+  int K;                       // (sh_deg+1)^2
+  int NH;                      // padded heads width, multiple of 16, <= 80
+  // ---- outputs ----
+  int out_mode;
+  float* out_rgb;              // OUT_RAW: [M, 3K] (reference channel-major order c*K+k)
+  float* out_sigma;            // OUT_RAW / OUT_SIGMA: [M]
+  float4* out_rgbs;            // OUT_RGBS: [M] (sigmoid(rgb), relu(sigma))
+  // ---- training saves (fast mode only; null = off) ----
+  uint8_t* save_h;             // [ntile][8][64 KB] activation tile images h_0..h_7
+  uint8_t* save_e;             // [ntile][16 KB]   posenc tile images
+  uint32_t* save_mask;         // [8][ntile*128][8] relu masks (bit i of word c = col 32c+i)
+};
+
+// padded heads width for K spherical-harmonic coefficients per channel
+inline int heads_width(int K) { return ((1 + 3 * K) + 15) / 16 * 16; }
+// bytes of one forward weight image (hi or lo)
+inline size_t fwd_image_bytes(int NH) { return size_t(60) * 16384 + size_t(8) * NH * 64; }
+// bytes of one dgrad weight image: heads (ceil(NH/32) slots) + layers 7..1 (8 slots each)
+inline size_t bwd_image_bytes(int NH) { return size_t((NH + 31) / 32 + 7 * 8) * 16384; }
+
+// precision: 1 = single fp16 pass (10-bit mantissa operands, fp32 accumulate),
+//            3 = error-compensated 3-pass split (hi*hi + lo*hi + hi*lo)
+cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int num_sms,
+                           cudaStream_t stream);
+
+// flat fp32 parameters of one MLP in reference order (Dense_0..Dense_9: kernel [in,out] then
+// bias) -> packed images.  `nparams` = param_count(K).
+cudaError_t launch_pack_weights(const float* flat, int K, uint8_t* w_hi, uint8_t* w_lo,
+                                uint8_t* wt_hi, float* bias, cudaStream_t stream);
+
+cudaError_t launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b_img,
+                              uint32_t b_bytes, uint32_t b_off, const uint64_t* adesc,
+                              const uint64_t* bdesc, const uint32_t* dcol, const uint32_t* accum,
+                              int nops, uint32_t idesc, int out_cols, float* out,
+                              cudaStream_t stream);
+
+// ---- flat parameter layout of one MLP (reference order) -------------------------------------
+// Dense_i kernel is [in,out] row-major (flax), followed by its bias [out].
+struct FlatLayout {
+  int w_off[10], b_off[10], in_dim[10], out_dim[10], total;
+};
+inline FlatLayout flat_layout(int K) {
+  FlatLayout L;
+  int off = 0;
+  for (int i = 0; i < 10; ++i) {
+    int in = (i == 0) ? 63 : (i == 5 ? 319 : 256);
+    int out = (i < 8) ? 256 : (i == 8 ? 1 : 3 * K);
+    L.in_dim[i] = in;
+    L.out_dim[i] = out;
+    L.w_off[i] = off;
+    off += in * out;
+    L.b_off[i] = off;
+    off += out;
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace pob

@@ -1,0 +1,491 @@
+// mlp_fwd.cu — fused NeRF-SH point evaluator for sm_100a.
+//
+// One persistent CTA per SM evaluates   posenc(x) -> 8 x (Dense256 + ReLU, skip-concat into
+// layer 5) -> [sigma | SH coefficient] heads -> (optionally) eval_sh at the view direction +
+// sigmoid/relu   for 256 samples per iteration, without the activations ever leaving the SM:
+//
+//   reference path                                      this kernel
+//   -------------------------------------------------   ------------------------------------
+//   model_utils.posenc      (model_utils.py:145-173)    epilogue warps -> E tile (smem, fp16)
+//   model_utils.MLP         (model_utils.py:30-94)      tcgen05.mma, fp32 accum in TMEM,
+//                                                       bias+ReLU epilogue TMEM->regs->smem
+//   sh.eval_sh + sigmoid/relu (sh.py:54-109,            heads epilogue (registers)
+//                              models.py:269-281)
+//   NerfModel.eval_points_raw (models.py:143-181)       OUT_RAW / OUT_SIGMA
+//
+// Warp roles (320 threads): warps 0-3 = epilogue group 0 (tile X), warps 4-7 = epilogue group 1
+// (tile Y), warp 8 = weight producer (cp.async.bulk ring, 4 x 16 KB slots), warp 9 = MMA issuer.
+// Both tiles consume every streamed weight slot (M = 256 per weight byte), TMEM holds the two
+// 128x256 fp32 accumulators (512 columns).  NSPLIT = 3 evaluates ONE tile per iteration with
+// error-compensated fp16 operands (x = hi + lo; hi*hi + lo*hi + hi*lo), using the second tile's
+// buffers for the residual parts.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pob {
+
+namespace {
+
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int FWD_THREADS = 320;
+
+// dynamic smem map
+constexpr uint32_t SM_A0 = 0;
+constexpr uint32_t SM_A1 = SM_A0 + A_TILE_BYTES;
+constexpr uint32_t SM_E0 = SM_A1 + A_TILE_BYTES;
+constexpr uint32_t SM_E1 = SM_E0 + E_TILE_BYTES;
+constexpr uint32_t SM_W = SM_E1 + E_TILE_BYTES;
+constexpr uint32_t SM_TOTAL = SM_W + NUM_WSLOTS * WSLOT_BYTES;  // 229376
+static_assert(SM_TOTAL == 224 * 1024, "smem map");
+
+struct Barriers {
+  uint64_t full[NUM_WSLOTS];
+  uint64_t empty[NUM_WSLOTS];
+  uint64_t a_ready[2];
+  uint64_t d_ready[2];
+};
+
+__device__ __forceinline__ void load_point(const FwdParams& p, long long s, float& x, float& y,
+                                           float& z) {
+  if (s >= p.M) s = p.M - 1;
+  if (p.src_mode == SRC_POINTS) {
+    const float* q = p.points + 3 * s;
+    x = __ldg(q);
+    y = __ldg(q + 1);
+    z = __ldg(q + 2);
+  } else if (p.src_mode == SRC_RAYS) {
+    long long r = s / p.n_per_ray;
+    float t = __ldg(p.zvals + s);
+    const float* o = p.origins + 3 * r;
+    const float* d = p.directions + 3 * r;
+    // cast_rays (model_utils.py:97-101): separate multiply and add, no FMA contraction
+    x = __fadd_rn(__ldg(o), __fmul_rn(t, __ldg(d)));
+    y = __fadd_rn(__ldg(o + 1), __fmul_rn(t, __ldg(d + 1)));
+    z = __fadd_rn(__ldg(o + 2), __fmul_rn(t, __ldg(d + 2)));
+  } else {
+    // extraction grid (octree/extraction.py:296-304): ((i + 0.5)/reso - offset)/scale
+    long long plane = (long long)p.g_ny * p.g_nz;
+    int ix = int(s / plane) + p.g_x0;
+    int rem = int(s % plane);
+    int iy = rem / p.g_nz;
+    int iz = rem % p.g_nz;
+    float inv = 1.0f / float(p.g_reso);  // reso is a power of two in the reference; see host check
+    float ax = __fmul_rn(__fadd_rn(float(ix), 0.5f), inv);
+    float ay = __fmul_rn(__fadd_rn(float(iy), 0.5f), inv);
+    float az = __fmul_rn(__fadd_rn(float(iz), 0.5f), inv);
+    x = __fdiv_rn(__fsub_rn(ax, p.g_offset[0]), p.g_scale[0]);
+    y = __fdiv_rn(__fsub_rn(ay, p.g_offset[1]), p.g_scale[1]);
+    z = __fdiv_rn(__fsub_rn(az, p.g_offset[2]), p.g_scale[2]);
+  }
+}
+
+// Positional encoding of one sample into the E tile(s).  Feature order (model_utils.py:162-173):
+// [x(3), sin(2^j x_c) j-major (30), sin(2^j x_c + pi/2) (30)], column 63 = 0.
+// unit_lo/unit_hi: which 16-byte units (8 features each) this thread stores.
+template <int NSPLIT, bool PRECISE>
+__device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row, float x, float y,
+                                           float z, int unit_lo, int unit_hi) {
+  float f[64];
+  f[0] = x;
+  f[1] = y;
+  f[2] = z;
+  const float xyz[3] = {x, y, z};
+  const float half_pi = 1.5707963267948966f;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const float sc = float(1 << j);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float xb = __fmul_rn(xyz[c], sc);
+      f[3 + 3 * j + c] = posenc_sin<PRECISE>(xb);
+      f[33 + 3 * j + c] = posenc_sin<PRECISE>(__fadd_rn(xb, half_pi));
+    }
+  }
+  f[63] = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if (u < unit_lo || u >= unit_hi) continue;
+    uint32_t w[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = f[8 * u + 2 * i], b = f[8 * u + 2 * i + 1];
+      w[i] = pack_f16x2(a, b);
+      if (NSPLIT == 3) {
+        float2 h = unpack_f16x2(w[i]);
+        wl[i] = pack_f16x2(a - h.x, b - h.y);
+      }
+    }
+    const uint32_t off = uint32_t(row) * 128u + (uint32_t(u ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(e_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (NSPLIT == 3) *reinterpret_cast<uint4*>(e_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  }
+}
+
+}  // namespace
+
+template <int NSPLIT, bool PRECISE>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) Barriers bars;
+  __shared__ uint32_t tmem_base_s;
+
+  constexpr int ROWS_PER_ITER = (NSPLIT == 1) ? 2 * TILE_M : TILE_M;
+  constexpr int NTILES = (NSPLIT == 1) ? 2 : 1;
+  const long long num_iters = (p.M + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const uint32_t sbase = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NUM_WSLOTS; ++i) {
+      mbar_init(smem_u32(&bars.full[i]), 1);
+      mbar_init(smem_u32(&bars.empty[i]), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&bars.a_ready[g]), NSPLIT == 1 ? 4 : 8);
+      mbar_init(smem_u32(&bars.d_ready[g]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == PRODUCER_WARP) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int NH = p.NH;
+
+  if (warp == PRODUCER_WARP) {
+    // =============================== weight producer ===================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+        size_t off = 0;
+        for (int l = 0; l <= NUM_TRUNK; ++l) {
+          const int ns = (l == NUM_TRUNK) ? 8 : fwd_slots_of_layer(l);
+          const uint32_t bytes = (l == NUM_TRUNK) ? uint32_t(NH) * 64u : uint32_t(WSLOT_BYTES);
+          for (int j = 0; j < ns; ++j) {
+#pragma unroll
+            for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); ++part) {
+              mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+              mbar_arrive_expect_tx(smem_u32(&bars.full[slot]), bytes);
+              bulk_g2s(sbase + SM_W + slot * WSLOT_BYTES, (part == 0 ? p.w.w_hi : p.w.w_lo) + off,
+                       bytes, smem_u32(&bars.full[slot]));
+              if (++slot == NUM_WSLOTS) {
+                slot = 0;
+                phase ^= 1;
+              }
+            }
+            off += bytes;
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================= MMA issuer ======================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, aphase = 0;
+      const uint32_t idesc_t = make_idesc_f16(TILE_M, WIDTH);
+      const uint32_t idesc_h = make_idesc_f16(TILE_M, NH);
+      constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
+      constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
+      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+        for (int l = 0; l <= NUM_TRUNK; ++l) {
+          const int ns = (l == NUM_TRUNK) ? 8 : fwd_slots_of_layer(l);
+          const uint32_t idesc = (l == NUM_TRUNK) ? idesc_h : idesc_t;
+          for (int j = 0; j < ns; ++j) {
+            const bool from_e = (l == 0) || (l == SKIP_LAYER && j >= 8);
+            const int kk = (l == SKIP_LAYER && j >= 8) ? j - 8 : j;
+            const uint32_t a_off = uint32_t(kk >> 1) * A_CHUNK_BYTES + uint32_t(kk & 1) * 64u;
+            const uint32_t s_hi = slot;
+            mbar_wait(smem_u32(&bars.full[s_hi]), phase);
+            uint32_t s_lo = 0;
+            if (NSPLIT == 3) {
+              s_lo = slot + 1;  // ring depth is even: hi/lo never straddle the wrap
+              mbar_wait(smem_u32(&bars.full[s_lo]), phase);
+            }
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < NTILES; ++g) {
+              if (j == 0) {
+                mbar_wait(smem_u32(&bars.a_ready[g]), aphase);
+                tc_fence_after();
+              }
+              const uint32_t a_base = sbase + (from_e ? (g ? SM_E1 : SM_E0) : (g ? SM_A1 : SM_A0)) + a_off;
+              const uint32_t d = tmem + uint32_t(g) * 256u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t acc = (j | ks) != 0;
+                if (NSPLIT == 1) {
+                  const uint64_t ad = A_HI | uint64_t(((a_base + ks * 32) >> 4) & 0x3FFF);
+                  const uint64_t bd =
+                      W_HI | uint64_t(((sbase + SM_W + s_hi * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
+                  umma_f16(d, ad, bd, idesc, acc);
+                } else {
+                  // tile 0 only: hi operand lives in the "tile 0" buffers, lo in the "tile 1" ones
+                  const uint32_t a_lo_base =
+                      sbase + (from_e ? SM_E1 : SM_A1) + a_off;
+                  const uint64_t ah = A_HI | uint64_t(((a_base + ks * 32) >> 4) & 0x3FFF);
+                  const uint64_t al = A_HI | uint64_t(((a_lo_base + ks * 32) >> 4) & 0x3FFF);
+                  const uint64_t bh =
+                      W_HI | uint64_t(((sbase + SM_W + s_hi * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
+                  const uint64_t bl =
+                      W_HI | uint64_t(((sbase + SM_W + s_lo * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
+                  umma_f16(d, al, bh, idesc, acc);
+                  umma_f16(d, ah, bl, idesc, 1u);
+                  umma_f16(d, ah, bh, idesc, 1u);
+                }
+              }
+              if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
+            }
+            umma_commit(smem_u32(&bars.empty[s_hi]));
+            if (NSPLIT == 3) umma_commit(smem_u32(&bars.empty[s_lo]));
+            slot += (NSPLIT == 3) ? 2 : 1;
+            if (slot == NUM_WSLOTS) {
+              slot = 0;
+              phase ^= 1;
+            }
+          }
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue warps ====================================
+    const int g = warp >> 2;                       // group
+    const int row = int((warp & 3) * 32 + lane);   // TMEM lane == tile row
+    const int tile_in_iter = (NSPLIT == 1) ? g : 0;
+    const int bar_id = (NSPLIT == 1) ? g : 0;
+    // column range of the trunk epilogue handled by this thread, in 32-column chunks
+    const int c_begin = (NSPLIT == 1) ? 0 : 4 * g;
+    const int c_end = (NSPLIT == 1) ? 8 : 4 * g + 4;
+    uint8_t* const a_hi = smem + ((NSPLIT == 1 && g == 1) ? SM_A1 : SM_A0);
+    uint8_t* const a_lo = smem + SM_A1;
+    uint8_t* const e_hi = smem + ((NSPLIT == 1 && g == 1) ? SM_E1 : SM_E0);
+    uint8_t* const e_lo = smem + SM_E1;
+    const int unit_lo = (NSPLIT == 1) ? 0 : 4 * g, unit_hi = (NSPLIT == 1) ? 8 : 4 * g + 4;
+    const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(tile_in_iter) * 256u;
+    const bool store_issuer = (NSPLIT == 1) && (warp & 3) == 0 && lane == 0;
+    const bool saving = (NSPLIT == 1) && (p.save_h != nullptr);
+    uint32_t dphase = 0;
+
+    auto signal_a_ready = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars.a_ready[bar_id]));
+    };
+
+    long long it = blockIdx.x;
+    if (it < num_iters) {
+      float x, y, z;
+      load_point(p, it * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
+      posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi);
+      signal_a_ready();
+    }
+    for (; it < num_iters; it += gridDim.x) {
+      const long long tile_idx = it * NTILES + tile_in_iter;
+      const long long s = tile_idx * TILE_M + row;
+      if (saving) {
+        // E tile of this iteration is complete (group-wide) once a_ready fired; make sure all 4
+        // warps of the group have written before the bulk store reads it.
+        named_bar_sync(1 + g, 128);
+        if (store_issuer) {
+          bulk_s2g(p.save_e + size_t(tile_idx) * E_TILE_BYTES, smem_u32(e_hi), E_TILE_BYTES);
+          bulk_commit();
+        }
+      }
+      // ------------------------------ trunk layers ------------------------------------
+      for (int l = 0; l < NUM_TRUNK; ++l) {
+        mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
+        dphase ^= 1;
+        tc_fence_after();
+        if (saving) {
+          if (store_issuer) bulk_wait_read_all();  // previous bulk stores finished reading smem
+          named_bar_sync(1 + g, 128);
+        }
+        const float* bias = p.w.bias + l * WIDTH;
+        uint32_t maskw[8];
+        constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          const int c = c_begin + cc;
+          uint32_t v[32];
+          tmem_ld32(d_tmem + c * 32, v);
+          tmem_ld_wait();
+          uint32_t mbits = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + u * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + u * 8 + 4));
+            float f[8];
+            f[0] = __uint_as_float(v[8 * u + 0]) + b0.x;
+            f[1] = __uint_as_float(v[8 * u + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * u + 2]) + b0.z;
+            f[3] = __uint_as_float(v[8 * u + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * u + 4]) + b1.x;
+            f[5] = __uint_as_float(v[8 * u + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * u + 6]) + b1.z;
+            f[7] = __uint_as_float(v[8 * u + 7]) + b1.w;
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = pack_f16x2_relu(f[2 * i], f[2 * i + 1]);
+            if (NSPLIT == 1 && saving) {
+              // relu mask: shift the (inverted) sign bit of each pre-activation into mbits;
+              // column 32c+i ends up at bit (31-i)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                mbits = __funnelshift_l(~__float_as_uint(f[i]), mbits, 1);
+            }
+            const uint32_t unit = uint32_t((c & 1) * 4 + u);
+            const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
+                                 ((unit ^ uint32_t(row & 7)) << 4);
+            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (NSPLIT == 3) {
+              uint32_t wl[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 h = unpack_f16x2(w[i]);
+                wl[i] = pack_f16x2(fmaxf(f[2 * i], 0.f) - h.x, fmaxf(f[2 * i + 1], 0.f) - h.y);
+              }
+              *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            }
+          }
+          maskw[cc] = mbits;
+        }
+        if (saving) {
+          if (NSPLIT == 1) {
+            const long long mrows = ((p.M + 2 * TILE_M - 1) / (2 * TILE_M)) * (2 * TILE_M);
+            uint4* mp = reinterpret_cast<uint4*>(p.save_mask + (size_t(l) * mrows + s) * 8);
+            mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
+            mp[1] = make_uint4(maskw[NCH - 4], maskw[NCH - 3], maskw[NCH - 2], maskw[NCH - 1]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + g, 128);
+          if (store_issuer) {
+            bulk_s2g(p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES, smem_u32(a_hi),
+                     A_TILE_BYTES);
+            bulk_commit();
+          }
+        }
+        signal_a_ready();
+        if (l == SKIP_LAYER) {
+          // E is dead until the next iteration: encode the next tile now, in the shadow of the
+          // layer-6/7/heads MMAs.
+          const long long nit = it + gridDim.x;
+          if (nit < num_iters) {
+            if (saving) {
+              if (store_issuer) bulk_wait_read_all();
+              named_bar_sync(1 + g, 128);
+            }
+            float x, y, z;
+            load_point(p, nit * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
+            posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi);
+            fence_proxy_async_smem();
+          }
+        }
+      }
+      // -------------------------------- heads ------------------------------------------
+      mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
+      dphase ^= 1;
+      tc_fence_after();
+      if (NSPLIT == 1 || g == 0) {
+        const float* bh = p.w.bias + NUM_TRUNK * WIDTH;
+        const int K = p.K;
+        float sigma_raw = 0.f;
+        float pre[3] = {0.f, 0.f, 0.f};
+        float basis[25];
+        float* stage = nullptr;
+        int P = 0;
+        if (p.out_mode == OUT_RGBS) {
+          long long sc = s < p.M ? s : p.M - 1;
+          long long vi = (p.src_mode == SRC_RAYS) ? sc / p.n_per_ray : sc;
+          const float* vd = p.viewdirs + 3 * vi;
+          if (p.sh_deg >= 0) sh_basis(p.sh_deg, __ldg(vd), __ldg(vd + 1), __ldg(vd + 2), basis);
+          else basis[0] = 1.f;
+        } else if (p.out_mode == OUT_RAW) {
+          // per-warp staging area inside this group's (now dead) activation tile
+          P = (3 * K) | 1;  // odd pitch (3K or 3K+1) -> conflict-free scalar stores
+          stage = reinterpret_cast<float*>(a_hi + (warp & 3) * 16384) + lane * P;
+        }
+#pragma unroll
+        for (int q = 0; q < MAX_NH / 16; ++q) {
+          if (q * 16 < NH) {
+            uint32_t v[16];
+            tmem_ld16(d_tmem + q * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int n = q * 16 + jj;
+              if (n == 0) {
+                sigma_raw = __uint_as_float(v[0]) + __ldg(bh);
+              } else {
+                const int k = (n - 1) / 3, c = (n - 1) % 3;
+                if (k < K) {
+                  const float coef = __uint_as_float(v[jj]) + __ldg(bh + n);
+                  if (p.out_mode == OUT_RGBS) pre[c] = fmaf(basis[k < 25 ? k : 24], coef, pre[c]);
+                  else if (p.out_mode == OUT_RAW) stage[c * K + k] = coef;
+                }
+              }
+            }
+          }
+        }
+        if (p.out_mode == OUT_RGBS) {
+          if (s < p.M) {
+            float4 o;
+            o.x = 1.f / (1.f + expf(-pre[0]));
+            o.y = 1.f / (1.f + expf(-pre[1]));
+            o.z = 1.f / (1.f + expf(-pre[2]));
+            o.w = fmaxf(sigma_raw, 0.f);
+            p.out_rgbs[s] = o;
+          }
+        } else {
+          if (s < p.M) p.out_sigma[s] = sigma_raw;
+          if (p.out_mode == OUT_RAW) {
+            __syncwarp();
+            const float* wstage = reinterpret_cast<const float*>(a_hi + (warp & 3) * 16384);
+            const long long row0 = tile_idx * TILE_M + (warp & 3) * 32;
+            const int C3 = 3 * K;
+            for (int rr = 0; rr < 32; ++rr) {
+              if (row0 + rr >= p.M) break;
+              for (int i = lane; i < C3; i += 32)
+                p.out_rgb[(row0 + rr) * C3 + i] = wstage[rr * P + i];
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // heads accumulator drained, next E tile already encoded (or this was the last iteration)
+      signal_a_ready();
+    }
+    if (saving && store_issuer) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PRODUCER_WARP) tmem_dealloc(tmem, 512);
+}
+
+cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int num_sms,
+                           cudaStream_t stream) {
+  if (p.M <= 0) return cudaSuccess;
+  const int rows = (nsplit == 1) ? 2 * TILE_M : TILE_M;
+  long long iters = (p.M + rows - 1) / rows;
+  int grid = int(iters < num_sms ? iters : num_sms);
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e =
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, FWD_THREADS, SM_TOTAL, stream>>>(p);
+    return cudaGetLastError();
+  };
+  if (nsplit == 1) {
+    return precise_sin ? launch(mlp_fwd_kernel<1, true>) : launch(mlp_fwd_kernel<1, false>);
+  } else if (nsplit == 3) {
+    return precise_sin ? launch(mlp_fwd_kernel<3, true>) : launch(mlp_fwd_kernel<3, false>);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace pob

@@ -1,0 +1,124 @@
+"""Generate the golden vectors under tests/golden/ by IMPORTING THE REFERENCE (read-only tree at
+/root/reference).  Runs only in the build container; the GPU box has no reference tree, it uses the
+committed .npz files.
+
+    python tests/golden/make_golden.py
+
+What is generated (all fp32, seeds fixed):
+  eval_points_sh16.npz / eval_points_sh25.npz
+      reference torch twin octree.nerf.models.NerfModel.eval_points_raw (octree/nerf/models.py:211)
+      on weights produced by oracle.init_flat_params(seed) (loaded into the twin's nn.Linear
+      modules, kernels transposed like octree/nerf/models.py:79-102 does for flax checkpoints).
+  eval_sh.npz      reference nerf_sh/nerf/sh.py::eval_sh for deg 0..4 on random coefficients/dirs.
+  posenc.npz       reference octree/nerf/model_utils.py::posenc.
+  rays.npz         reference octree/nerf/utils.py::generate_rays on two spherical poses.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import nerf_sh_oracle as O  # noqa: E402
+
+
+def load_ref_module(name, relpath):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def ref_model(sh_deg, flat_c, flat_f):
+    from octree.nerf import models as ref_models
+    K = (sh_deg + 1) ** 2
+    model = ref_models.NerfModel(use_viewdirs=False, sh_deg=sh_deg, num_rgb_channels=3 * K,
+                                 num_coarse_samples=64, num_fine_samples=128)
+    for name, flat in (("MLP_0", flat_c), ("MLP_1", flat_f)):
+        mlp = getattr(model, name)
+        params = O.unflatten(flat, sh_deg)
+        with torch.no_grad():
+            for i in range(8):
+                mlp.input_layers[i].weight.copy_(params[i][0].T)
+                mlp.input_layers[i].bias.copy_(params[i][1])
+            mlp.sigma_layer.weight.copy_(params[8][0].T)
+            mlp.sigma_layer.bias.copy_(params[8][1])
+            mlp.rgb_layer.weight.copy_(params[9][0].T)
+            mlp.rgb_layer.bias.copy_(params[9][1])
+    return model.eval()
+
+
+def gen_eval_points(sh_deg, n, seed, fname):
+    flat_c = O.init_flat_params(sh_deg, seed, bias_scale=0.05)
+    flat_f = O.init_flat_params(sh_deg, seed + 1, bias_scale=0.05)
+    rs = np.random.RandomState(seed + 2)
+    pts = rs.uniform(-1.5, 1.5, size=(n, 3)).astype(np.float32)
+    pts[: n // 8] *= 3.0  # far points (|x| up to 4.5) stress the 2^9 posenc octave
+    pts[0] = 0.0
+    model = ref_model(sh_deg, flat_c, flat_f)
+    with torch.no_grad():
+        rgb_f, sig_f = model.eval_points_raw(torch.from_numpy(pts))
+        rgb_c, sig_c = model.eval_points_raw(torch.from_numpy(pts), coarse=True)
+    np.savez_compressed(os.path.join(HERE, fname), sh_deg=sh_deg, seed=seed, points=pts,
+                        raw_rgb_fine=rgb_f.numpy(), raw_sigma_fine=sig_f.numpy(),
+                        raw_rgb_coarse=rgb_c.numpy(), raw_sigma_coarse=sig_c.numpy(),
+                        flat_c_checksum=np.float64(flat_c.astype(np.float64).sum()),
+                        flat_f_checksum=np.float64(flat_f.astype(np.float64).sum()))
+    print(fname, rgb_f.shape, float(sig_f.abs().mean()))
+
+
+def gen_eval_sh():
+    ref_sh = load_ref_module("ref_sh", "nerf_sh/nerf/sh.py")
+    rs = np.random.RandomState(7)
+    out = {}
+    for deg in range(5):
+        K = (deg + 1) ** 2
+        sh = rs.normal(size=(64, 3, K)).astype(np.float32)
+        d = rs.normal(size=(64, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        out[f"sh{deg}"] = sh
+        out[f"dirs{deg}"] = d
+        out[f"res{deg}"] = ref_sh.eval_sh(deg, sh, d).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "eval_sh.npz"), **out)
+    print("eval_sh.npz")
+
+
+def gen_posenc():
+    from octree.nerf import model_utils as ref_mu
+    rs = np.random.RandomState(11)
+    x = rs.uniform(-4, 4, size=(256, 3)).astype(np.float32)
+    enc = ref_mu.posenc(torch.from_numpy(x), 0, 10).numpy()
+    np.savez_compressed(os.path.join(HERE, "posenc.npz"), x=x, enc=enc)
+    print("posenc.npz", enc.shape)
+
+
+def gen_rays():
+    ref_utils = load_ref_module("ref_octree_utils", "octree/nerf/utils.py")
+    poses = np.stack([O.pose_spherical(30.0, -30.0, 4.0), O.pose_spherical(-120.0, -75.0, 4.0)])
+    w, h, focal = 40, 30, 55.5
+    rays = ref_utils.generate_rays(w, h, focal, poses)
+    np.savez_compressed(os.path.join(HERE, "rays.npz"), poses=poses, w=w, h=h, focal=focal,
+                        origins=np.asarray(rays.origins), directions=np.asarray(rays.directions),
+                        viewdirs=np.asarray(rays.viewdirs))
+    print("rays.npz")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(20200823)
+    torch.set_num_threads(8)
+    gen_eval_points(3, 2048, 20200823, "eval_points_sh16.npz")
+    gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
+    gen_eval_sh()
+    gen_posenc()
+    try:
+        gen_rays()
+    except Exception as e:  # octree/nerf/utils.py pulls optional deps
+        print("rays.npz skipped:", repr(e))
