@@ -78,6 +78,86 @@ int pob_eval_points_raw_host(const void* packed_dev, int sh_deg, const float* po
                              int precision);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-ray stages (exposed individually for parity tests; pob_render_rays chains them).
+ * ------------------------------------------------------------------------------------------- */
+/* model_utils.sample_along_rays (nerf_sh/nerf/model_utils.py:104-142).  z_base[n_samples] is the
+ * un-jittered table near*(1-t)+far*t (or the lindisp form) built by the host with the reference
+ * expression; t_rand [n_rays,n_samples] in [0,1) replaces random.uniform (NULL = randomized False). */
+int pob_sample_coarse(const float* z_base_dev, const float* t_rand_dev, int n_rays, int n_samples,
+                      float* z_out_dev, void* stream);
+/* model_utils.volumetric_rendering (model_utils.py:176-222).  rgbs [n_rays,n_samples,4] = (rgb, sigma)
+ * after activations; outputs comp_rgb [n_rays,3], disp, acc [n_rays], weights [n_rays,n_samples]
+ * (disp / acc / weights may be NULL). */
+int pob_composite(const float* rgbs_dev, const float* z_dev, const float* dirs_dev, int n_rays, int n_samples,
+                  int white_bkgd, float* out_rgb_dev, float* out_disp_dev, float* out_acc_dev,
+                  float* out_weights_dev, void* stream);
+/* reverse-mode of pob_composite composed with the MSE of loss_fn (nerf_sh/train.py:86-96) and with
+ * sigmoid'/relu': g_out [n_rays,n_samples,4] = d/d(pre-activation rgb after eval_sh, raw sigma) of
+ * gscale/2 * sum (comp_rgb - pixels)^2;  sq_err_sum_dev (may be NULL) += sum (comp_rgb - pixels)^2. */
+int pob_composite_bwd(const float* rgbs_dev, const float* z_dev, const float* dirs_dev, const float* comp_rgb_dev,
+                      const float* pixels_dev, int n_rays, int n_samples, int white_bkgd, float gscale,
+                      float* g_out_dev, float* sq_err_sum_dev, void* stream);
+/* model_utils.sample_pdf (model_utils.py:225-314): inverse-CDF resampling from weights[...,1:-1] over the
+ * mid-point bins, then the sorted union with the coarse depths.  u: [n_fine] table (u_per_ray = 0,
+ * randomized False: linspace(0, 1-eps)) or [n_rays,n_fine] uniforms.  z_out [n_rays, n_coarse+n_fine]. */
+int pob_sample_pdf(const float* z_coarse_dev, const float* weights_dev, const float* u_dev, int u_per_ray,
+                   int n_rays, int n_coarse, int n_fine, float* z_out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NerfModel.__call__(rng_0, rng_1, rays, randomized) -> [(rgb,disp,acc)_coarse, (rgb,disp,acc)_fine]
+ *   nerf_sh/nerf/models.py:216-348   (callers: train.py:70, utils.render_image utils.py:331-381)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pob_render_config {
+  int sh_deg;               /* flag sh_deg            (nerf_sh/nerf/utils.py:135) */
+  int num_coarse_samples;   /* flag num_coarse_samples (utils.py:126)             */
+  int num_fine_samples;     /* flag num_fine_samples   (utils.py:130); 0 = single level */
+  int white_bkgd;           /* flag white_bkgd */
+  int max_rays;             /* capacity of the workspace in rays per call */
+  int sparsity_npoints;     /* flag sparsity_npoints (training workspace only) */
+} pob_render_config;
+
+/* bytes of device scratch the render (training=0) / training (training=1) calls need */
+int64_t pob_workspace_bytes(const pob_render_config* cfg, int training);
+
+/* out_coarse / out_fine: [n_rays,5] = (r,g,b,disp,acc).  t_rand NULL = randomized False.
+ * z_fine_dev (normally NULL): [n_rays, Nc+Nf] sorted depths that replace the sample_pdf stage — lets a
+ * caller (and the parity tests) pin the fine-level sample positions. */
+int pob_render_rays(const pob_render_config* cfg, const void* packed_coarse_dev, const void* packed_fine_dev,
+                    const float* origins_dev, const float* directions_dev, const float* viewdirs_dev,
+                    int n_rays, const float* z_base_dev, const float* t_rand_dev, const float* u_dev,
+                    int u_per_ray, const float* z_fine_dev, float* out_coarse_dev, float* out_fine_dev,
+                    void* workspace_dev, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * train_step (nerf_sh/train.py:51-121), split at the gradient all-reduce:
+ *   pob_loss_and_grad = jax.value_and_grad(loss_fn)   (train.py:66-116)
+ *   [caller: all-reduce-mean of grad_flat over ranks   (train.py:117) ]
+ *   pob_adam_update   = optimizer.apply_gradient       (train.py:119) + operand re-pack
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pob_train_hparams {
+  float sparsity_weight;    /* flag sparsity_weight (utils.py:191) ; 0 disables the term */
+  float sparsity_length;    /* flag sparsity_length */
+  float loss_scale;         /* power-of-two scale applied to the fp16 gradient chain, divided out of grad_flat */
+} pob_train_hparams;
+
+/* grad_flat [num_mlps * pob_param_count] (MLP_0 then MLP_1, reference flat order), per-rank gradient of
+ *   mean((rgb_f-px)^2) + mean((rgb_c-px)^2) + sparsity_weight*(1-mean(exp(-len*relu(sigma(p)))))
+ * stats [8] (device): [0] sum (rgb_fine-px)^2, [1] sum (rgb_coarse-px)^2, [2] sum exp(-len*relu(sigma)). */
+int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp, const void* packed_coarse_dev,
+                      const void* packed_fine_dev, const float* origins_dev, const float* directions_dev,
+                      const float* viewdirs_dev, const float* pixels_dev, int n_rays, const float* z_base_dev,
+                      const float* t_rand_dev, const float* u_dev, int u_per_ray, const float* z_fine_dev,
+                      const float* sp_points_dev, float* grad_flat_dev, float* stats_dev, void* workspace_dev,
+                      void* stream);
+
+/* flax.optim.Adam (beta1 .9, beta2 .999, eps 1e-8; nerf_sh/nerf/models.py:44) on the flat buffers of
+ * num_mlps MLPs, g = grad*grad_mult + weight_decay_coef*param, then re-packs the operand blobs.
+ * `step` = number of updates already applied (flax optimizer.state.step). */
+int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* grads_dev, float* m_dev,
+                    float* v_dev, float lr, float step, float grad_mult, float weight_decay_coef,
+                    void* packed_coarse_dev, void* packed_fine_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Test bench for the tcgen05 descriptor conventions (tests/test_umma_probe.py).
  * Runs `nops` tcgen05.mma (kind::f16, M=128) on two shared-memory images and returns the
  * [128 x out_cols] fp32 accumulator.

@@ -28,8 +28,27 @@ SIGNATURES = {
     "pob_eval_grid": (_i, [_vp, _i, _i, _i, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
                            _fp, _fp, _i, _vp]),
     "pob_eval_points_raw_host": (_i, [_vp, _i, _fp, _i64, _fp, _fp, _i]),
+    "pob_sample_coarse": (_i, [_fp, _fp, _i, _i, _fp, _vp]),
+    "pob_composite": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
+    "pob_composite_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _c.c_float, _fp, _fp, _vp]),
+    "pob_sample_pdf": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _vp]),
+    "pob_workspace_bytes": (_i64, [_vp, _i]),
+    "pob_render_rays": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _i, _vp]),
+    "pob_loss_and_grad": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _fp,
+                               _vp, _vp]),
+    "pob_adam_update": (_i, [_i, _i, _fp, _fp, _fp, _fp, _c.c_float, _c.c_float, _c.c_float, _c.c_float,
+                             _vp, _vp, _vp]),
     "pob_umma_probe": (_i, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i, _u32, _i, _fp, _vp]),
 }
+
+
+class RenderConfig(_c.Structure):
+    _fields_ = [("sh_deg", _i), ("num_coarse_samples", _i), ("num_fine_samples", _i), ("white_bkgd", _i),
+                ("max_rays", _i), ("sparsity_npoints", _i)]
+
+
+class TrainHParams(_c.Structure):
+    _fields_ = [("sparsity_weight", _c.c_float), ("sparsity_length", _c.c_float), ("loss_scale", _c.c_float)]
 
 
 class PobError(RuntimeError):

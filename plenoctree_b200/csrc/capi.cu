@@ -4,24 +4,22 @@
 #include <string>
 
 #include "../../include/plenoctree_b200.h"
+#include "capi_util.h"
 #include "common.cuh"
 #include "kernels.h"
 
-namespace {
+static thread_local std::string g_err = "";
 
-thread_local std::string g_err = "";
-
-int fail(const char* where, const char* what) {
+int pob_fail(const char* where, const char* what) {
   g_err = std::string(where) + ": " + what;
   return 1;
 }
-int cuda_fail(const char* where, cudaError_t e) { return fail(where, cudaGetErrorString(e)); }
+int pob_cuda_fail(const char* where, cudaError_t e) { return pob_fail(where, cudaGetErrorString(e)); }
 
-#define POB_CUDA(where, call)                       \
-  do {                                              \
-    cudaError_t _e = (call);                        \
-    if (_e != cudaSuccess) return cuda_fail(where, _e); \
-  } while (0)
+namespace {
+
+int fail(const char* where, const char* what) { return pob_fail(where, what); }
+int cuda_fail(const char* where, cudaError_t e) { return pob_cuda_fail(where, e); }
 
 int K_of(int sh_deg) { return sh_deg < 0 ? 1 : (sh_deg + 1) * (sh_deg + 1); }
 
@@ -88,6 +86,12 @@ pob::FwdParams base_params(const void* packed, int sh_deg) {
 }
 
 }  // namespace
+
+int pob_sm_count_cached() { return sm_count(); }
+int pob_check_common(const char* where, const void* packed, int sh_deg, int precision) {
+  return check_common(where, packed, sh_deg, precision);
+}
+pob::FwdParams pob_base_params(const void* packed, int sh_deg) { return base_params(packed, sh_deg); }
 
 extern "C" {
 
@@ -223,6 +227,50 @@ int pob_eval_points_raw_host(const void* packed_dev, int sh_deg, const float* po
   cudaFree(d_rgb);
   cudaFree(d_sig);
   return rc;
+}
+
+int pob_sample_coarse(const float* z_base_dev, const float* t_rand_dev, int n_rays, int n_samples,
+                      float* z_out_dev, void* stream) {
+  if (!z_base_dev || !z_out_dev) return fail("pob_sample_coarse", "NULL pointer");
+  if (n_rays < 0 || n_samples < 1) return fail("pob_sample_coarse", "bad sizes");
+  POB_CUDA("pob_sample_coarse",
+           pob::launch_sample_coarse(z_base_dev, t_rand_dev, n_rays, n_samples, z_out_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int pob_composite(const float* rgbs_dev, const float* z_dev, const float* dirs_dev, int n_rays, int n_samples,
+                  int white_bkgd, float* out_rgb_dev, float* out_disp_dev, float* out_acc_dev,
+                  float* out_weights_dev, void* stream) {
+  if (!rgbs_dev || !z_dev || !dirs_dev || !out_rgb_dev) return fail("pob_composite", "NULL pointer");
+  if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail("pob_composite", "n_samples must be in [1,256]");
+  POB_CUDA("pob_composite",
+           pob::launch_composite_fwd(reinterpret_cast<const float4*>(rgbs_dev), z_dev, dirs_dev, n_rays, n_samples,
+                                     white_bkgd, out_rgb_dev, out_disp_dev, out_acc_dev, out_weights_dev,
+                                     (cudaStream_t)stream));
+  return 0;
+}
+
+int pob_composite_bwd(const float* rgbs_dev, const float* z_dev, const float* dirs_dev, const float* comp_rgb_dev,
+                      const float* pixels_dev, int n_rays, int n_samples, int white_bkgd, float gscale,
+                      float* g_out_dev, float* sq_err_sum_dev, void* stream) {
+  if (!rgbs_dev || !z_dev || !dirs_dev || !comp_rgb_dev || !pixels_dev || !g_out_dev)
+    return fail("pob_composite_bwd", "NULL pointer");
+  if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail("pob_composite_bwd", "n_samples must be in [1,256]");
+  POB_CUDA("pob_composite_bwd",
+           pob::launch_composite_bwd(reinterpret_cast<const float4*>(rgbs_dev), z_dev, dirs_dev, comp_rgb_dev,
+                                     pixels_dev, n_rays, n_samples, white_bkgd, gscale,
+                                     reinterpret_cast<float4*>(g_out_dev), sq_err_sum_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int pob_sample_pdf(const float* z_coarse_dev, const float* weights_dev, const float* u_dev, int u_per_ray,
+                   int n_rays, int n_coarse, int n_fine, float* z_out_dev, void* stream) {
+  if (!z_coarse_dev || !weights_dev || !u_dev || !z_out_dev) return fail("pob_sample_pdf", "NULL pointer");
+  if (n_coarse < 3 || n_fine < 1 || n_coarse + n_fine > 256)
+    return fail("pob_sample_pdf", "need n_coarse >= 3 and n_coarse + n_fine <= 256");
+  POB_CUDA("pob_sample_pdf", pob::launch_sample_pdf(z_coarse_dev, weights_dev, u_dev, u_per_ray, n_rays, n_coarse,
+                                                    n_fine, z_out_dev, (cudaStream_t)stream));
+  return 0;
 }
 
 int pob_umma_probe(const void* a_img_dev, uint32_t a_bytes, const void* b_img_dev,

@@ -69,6 +69,64 @@ cudaError_t launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b
                               int nops, uint32_t idesc, int out_cols, float* out,
                               cudaStream_t stream);
 
+
+// ---- render.cu ------------------------------------------------------------------------------
+cudaError_t launch_sample_coarse(const float* z_base, const float* t_rand, int R, int N, float* z_out,
+                                 cudaStream_t st);
+cudaError_t launch_composite_fwd(const float4* rgbs, const float* z, const float* dirs, int R, int N,
+                                 int white_bkgd, float* out_rgb, float* out_disp, float* out_acc,
+                                 float* out_weights, cudaStream_t st);
+cudaError_t launch_composite_bwd(const float4* rgbs, const float* z, const float* dirs,
+                                 const float* comp_rgb, const float* pixels, int R, int N, int white_bkgd,
+                                 float gscale, float4* G, float* sq_err_sum, cudaStream_t st);
+cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const float* u, int u_per_ray, int R,
+                              int Nc, int Nf, float* z_out, cudaStream_t st);
+cudaError_t launch_sparsity_grad(const float* sigma_raw, int n, float length, float coef, float4* G,
+                                 float* exp_sum, cudaStream_t st);
+
+// ---- mlp_bwd.cu -----------------------------------------------------------------------------
+struct BwdParams {
+  long long M;
+  const float4* G;          // [M] (d pre_r, d pre_g, d pre_b, d sigma_raw), loss-scaled
+  const float* viewdirs;    // [R,3] (n_per_ray > 0) or [M,3] (n_per_ray == 0)
+  int n_per_ray;
+  MlpPacked w;
+  int sh_deg, K, NH;
+  const uint32_t* mask;     // [8][Mpad][8] from mlp_fwd
+  uint8_t* save_dz;         // [ntile][8][64 KB]
+  uint8_t* save_do;         // [ntile][32 KB]
+};
+cudaError_t launch_mlp_bwd(const BwdParams& p, int num_sms, cudaStream_t stream);
+
+// ---- mlp_wgrad.cu ---------------------------------------------------------------------------
+constexpr int WG_PARTIAL_FLOATS = 65536 + 256;
+constexpr int WG_MAX_CTAS = 160;
+constexpr int WG_NUM_ROLES = 10;
+struct WgradSegment {
+  const uint8_t *h, *dz, *e, *d_o;
+};
+struct WgradParams {
+  WgradSegment seg[2];
+  long long seg_tiles[2];
+  int NH;
+  float* partials;          // [num_ctas][WG_PARTIAL_FLOATS]
+  short cta_role[WG_MAX_CTAS], cta_index[WG_MAX_CTAS], cta_count[WG_MAX_CTAS];
+};
+// role -> [first CTA, count]; fills the per-CTA tables of `p`; returns number of CTAs to launch
+int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES],
+                       int role_count[WG_NUM_ROLES]);
+cudaError_t launch_mlp_wgrad(const WgradParams& p, int num_ctas, cudaStream_t stream);
+
+// ---- optim.cu -------------------------------------------------------------------------------
+// partials of one wgrad launch -> flat gradient of one MLP (reference layout), times inv_scale
+cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_NUM_ROLES],
+                                const int role_count[WG_NUM_ROLES], int K, float inv_scale,
+                                float* grad_flat, cudaStream_t stream);
+// flax.optim.Adam.apply_gradient on a flat buffer; grad is multiplied by grad_mult first
+cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                        float step, float beta1, float beta2, float eps, float grad_mult,
+                        float weight_decay_coef, cudaStream_t stream);
+
 // ---- flat parameter layout of one MLP (reference order) -------------------------------------
 // Dense_i kernel is [in,out] row-major (flax), followed by its bias [out].
 struct FlatLayout {

@@ -1,0 +1,168 @@
+"""GPU parity of value_and_grad(loss_fn) + Adam against the CPU oracle's autograd."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _record(name, payload):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, "parity_train.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = payload
+    json.dump(data, open(path, "w"), indent=1)
+
+
+def _setup(sh_deg, R, nf, nsp, seed):
+    from oracle import nerf_sh_oracle as O
+    from tests.test_render import _rays
+    fc = O.init_flat_params(sh_deg, seed, bias_scale=0.05)
+    ff = O.init_flat_params(sh_deg, seed + 1, bias_scale=0.05)
+    K = (sh_deg + 1) ** 2
+    for f in (fc, ff):
+        off = O.param_count(sh_deg) - 3 * K - 1 - 256 * 3 * K - 256
+        f[off:off + 256] *= 30.0
+    o, d, v = _rays(R, seed)
+    rs = np.random.RandomState(seed)
+    px = rs.uniform(0, 1, size=(R, 3)).astype(np.float32)
+    t_rand = rs.uniform(0, 1, size=(R, 64)).astype(np.float32)
+    u = rs.uniform(0, 1, size=(R, nf)).astype(np.float32) if nf else None
+    sp = rs.uniform(-1.5, 1.5, size=(nsp, 3)).astype(np.float32) if nsp else None
+    return fc, ff, (o, d, v), px, t_rand, u, sp
+
+
+def _layer_report(g, ref, sh_deg):
+    from plenoctree_b200 import layouts as L
+    w_off, b_off, total = L.flat_offsets(L.K_of(sh_deg))
+    dims = L.layer_dims(L.K_of(sh_deg))
+    rep = {}
+    for i, (cin, cout) in enumerate(dims):
+        for nm, a, n in (("w", w_off[i], cin * cout), ("b", b_off[i], cout)):
+            x, y = g[a:a + n], ref[a:a + n]
+            rel = float(np.linalg.norm(x - y) / max(1e-30, np.linalg.norm(y)))
+            rep[f"Dense_{i}.{nm}"] = rel
+    return rep
+
+
+@pytest.mark.parametrize("sh_deg,R,nf,nsp", [(3, 96, 128, 300), (3, 64, 0, 0), (4, 40, 128, 64)])
+def test_loss_and_grad_vs_oracle(sh_deg, R, nf, nsp):
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf import train as T
+    fc, ff, rays, px, t_rand, u, sp = _setup(sh_deg, R, nf, nsp, 77)
+    cfg = dict(num_coarse_samples=64, num_fine_samples=nf, near=2.0, far=6.0, white_bkgd=True,
+               sparsity_weight=1e-3 if nsp else 0.0, sparsity_length=0.05)
+    stats_o, gc_o, gf_o = O.loss_and_grads(fc, ff, sh_deg, rays, px, cfg, t_rand, u, sp)
+    stats_o.pop("_z_fine")
+    model = NerfModel(sh_deg=sh_deg, num_coarse_samples=64, num_fine_samples=nf, max_rays=R, sparsity_npoints=nsp)
+    model.set_params(np.concatenate([fc, ff]) if nf else fc)
+    state = T.TrainState(model)
+    batch = {"rays": Rays(*rays), "pixels": px}
+    n = T.loss_and_grad(model, state, batch, sparsity_weight=cfg["sparsity_weight"], sparsity_length=0.05,
+                        randomized=True, t_rand=t_rand, u=u, sp_points=sp)
+    torch.cuda.synchronize()
+    g = state.grads.cpu().numpy()
+    assert np.isfinite(g).all()
+    P = model.P
+    rep = {"MLP_0": _layer_report(g[:P], gc_o, sh_deg)}
+    if nf:
+        rep["MLP_1"] = _layer_report(g[P:], gf_o, sh_deg)
+    st = T.stats_from_raw(state.stats_raw, n, cfg["sparsity_weight"], nsp, nf > 0)
+    rep["stats"] = dict(gpu=st._asdict(), oracle=stats_o)
+    _record(f"sh{sh_deg}_R{R}_nf{nf}_nsp{nsp}", rep)
+    # loss values (fp16 forward): 2e-3 relative
+    assert abs(st.loss - stats_o["loss"]) / stats_o["loss"] < 2e-3
+    if nf:
+        assert abs(st.loss_c - stats_o["loss_c"]) / stats_o["loss_c"] < 2e-3
+    if nsp:
+        assert abs(st.loss_sp - stats_o["loss_sp"]) < 2e-3 * max(abs(stats_o["loss_sp"]), 1e-6) + 1e-7
+    # (a) against the fp32 oracle, free running.  fp16 operands flip ~4e-4 of the ReLU masks and move the
+    # fine-level samples, so early layers carry per-tensor errors of a few percent on a random-init field;
+    # the bar is on the whole gradient: relative L2 < 2e-2, cosine > 0.9995, and tight heads for MLP_0.
+    ref_all = np.concatenate([gc_o, gf_o]) if nf else gc_o
+    tot = float(np.linalg.norm(g - ref_all) / np.linalg.norm(ref_all))
+    cos = float(np.dot(g, ref_all) / (np.linalg.norm(g) * np.linalg.norm(ref_all)))
+    _record(f"sh{sh_deg}_R{R}_nf{nf}_nsp{nsp}_total", dict(rel_l2=tot, cosine=cos))
+    assert tot < 2e-2 and cos > 0.9995, (tot, cos)
+    assert rep["MLP_0"]["Dense_9.w"] < 5e-3 and rep["MLP_0"]["Dense_8.w"] < 5e-3
+    # (b) against the oracle with the SAME operand precision (fp16-rounded GEMM operands, fp32 accumulate,
+    # loss-scaled fp16 gradient chain) and the same fine-level depths: isolates kernel logic from precision.
+    # Even this emulation is chaotic at the percent level for the early layers: a pre-activation within
+    # rounding distance of zero flips its ReLU mask, and the emulation evaluated in fp32 vs fp64 already
+    # differs by ~2e-2 on Dense_0 (measured; DESIGN.md "gradient parity").  Bars: heads < 1e-2 (no mask
+    # upstream of them flips the result), trunk tensors < 0.1, whole gradient < 2e-2.
+    scale = T.default_loss_scale(R)
+    with O.emulate_fp16_operands(loss_scale=scale):
+        stats_e, gc_e, gf_e = O.loss_and_grads(fc, ff, sh_deg, rays, px, cfg, t_rand, u, sp)
+    T.loss_and_grad(model, state, batch, sparsity_weight=cfg["sparsity_weight"], sparsity_length=0.05,
+                    randomized=True, t_rand=t_rand, u=u, sp_points=sp, z_fine=stats_e["_z_fine"])
+    torch.cuda.synchronize()
+    g2 = state.grads.cpu().numpy()
+    rep2 = {"MLP_0": _layer_report(g2[:P], gc_e, sh_deg)}
+    if nf:
+        rep2["MLP_1"] = _layer_report(g2[P:], gf_e, sh_deg)
+    _record(f"sh{sh_deg}_R{R}_nf{nf}_nsp{nsp}_vs_fp16_emulation", rep2)
+    ref_e = np.concatenate([gc_e, gf_e]) if nf else gc_e
+    tot_e = float(np.linalg.norm(g2 - ref_e) / np.linalg.norm(ref_e))
+    _record(f"sh{sh_deg}_R{R}_nf{nf}_nsp{nsp}_vs_fp16_emulation_total", dict(rel_l2=tot_e))
+    assert tot_e < 2e-2, tot_e
+    for mlp in rep2:
+        for name, rel in rep2[mlp].items():
+            bar = 1e-2 if name.startswith(("Dense_8", "Dense_9")) else 0.1
+            assert rel < bar, (mlp, name, rel)
+
+
+def test_adam_update_and_repack():
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf.models import NerfModel
+    from plenoctree_b200.nerf import train as T
+    from plenoctree_b200._lib import check, lib, ptr
+    sh_deg = 3
+    model = NerfModel(sh_deg=sh_deg, max_rays=64)
+    model.init_params(3)
+    state = T.TrainState(model)
+    rs = np.random.RandomState(0)
+    p = model.params.cpu().numpy().copy()
+    m = np.zeros_like(p)
+    v = np.zeros_like(p)
+    for step in range(3):
+        g = (rs.normal(size=p.shape) * 1e-3).astype(np.float32)
+        state.grads.copy_(torch.from_numpy(g))
+        check(lib.pob_adam_update(sh_deg, 2, ptr(model.params), ptr(state.grads), ptr(state.m), ptr(state.v),
+                                  5e-4, float(step), 0.5, 0.0, ptr(model.blobs[0]), ptr(model.blobs[1]), None))
+        p, m, v = O.adam_step(p, 0.5 * g, m, v, float(step), 5e-4)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(model.params.cpu().numpy(), p, rtol=2e-5, atol=1e-7)
+    # the packed blob follows the new parameters
+    from plenoctree_b200 import ops
+    pts = torch.from_numpy(rs.uniform(-1, 1, size=(300, 3)).astype(np.float32)).cuda()
+    rgb, sig = model.eval_points_raw(pts, precision=ops.PREC_FP16X3)
+    with torch.no_grad():
+        rgb_o, sig_o = O.eval_points_raw(O.unflatten(p[model.P:], sh_deg), pts.cpu())
+    assert float((rgb.cpu() - rgb_o).abs().max() / rgb_o.abs().max()) < 1e-4
+
+
+def test_training_reduces_loss():
+    """a few hundred steps on a fixed synthetic batch: the loss must go down (teacher = constant colour)."""
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf import train as T
+    from tests.test_render import _rays
+    R = 512
+    o, d, v = _rays(R, 4)
+    px = np.tile(np.array([[0.8, 0.3, 0.1]], np.float32), (R, 1))
+    model = NerfModel(sh_deg=3, max_rays=R, sparsity_npoints=1000)
+    model.init_params(1)
+    state = T.TrainState(model)
+    batch = {"rays": Rays(o, d, v), "pixels": px}
+    first = T.train_step(model, state, batch, 5e-4, sync_stats=True)
+    for _ in range(60):
+        T.train_step(model, state, batch, 5e-4)
+    last = T.train_step(model, state, batch, 5e-4, sync_stats=True)
+    assert np.isfinite(last.loss) and last.loss < 0.5 * first.loss, (first, last)
