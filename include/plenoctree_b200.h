@@ -36,6 +36,14 @@ const char* pob_last_error(void);
 /* number of SMs of the current CUDA device (persistent-grid size); <0 on error */
 int pob_sm_count(void);
 
+/* Instrumentation used by bench.py: number of kernels this library has launched so far, and
+ * optional CUDA-event timing per kernel class.  pob_timing_read fills ms_out[5] / launches_out[5] for
+ * {mlp_fwd, mlp_bwd, mlp_wgrad, per-ray render stages, optimiser (reduce, Adam, pack)} and returns 5;
+ * it synchronises with the recorded events. */
+long long pob_launch_count(void);
+void pob_timing_enable(int on);
+int pob_timing_read(double* ms_out, long long* launches_out);
+
 /* ---------------------------------------------------------------------------------------------
  * Parameters of one MLP (MLP_0 coarse / MLP_1 fine; nerf_sh/nerf/models.py:83-104).
  * Flat fp32 layout = Dense_0..Dense_9 in order, each kernel [in,out] row-major then bias [out]

@@ -20,6 +20,9 @@ SIGNATURES = {
     "pob_abi_version": (_i, []),
     "pob_last_error": (_c.c_char_p, []),
     "pob_sm_count": (_i, []),
+    "pob_launch_count": (_c.c_longlong, []),
+    "pob_timing_enable": (None, [_i]),
+    "pob_timing_read": (_i, [_vp, _vp]),
     "pob_param_count": (_i64, [_i]),
     "pob_packed_bytes": (_i64, [_i]),
     "pob_pack_weights": (_i, [_fp, _i, _vp, _vp]),

@@ -16,6 +16,46 @@ int pob_fail(const char* where, const char* what) {
 }
 int pob_cuda_fail(const char* where, cudaError_t e) { return pob_fail(where, cudaGetErrorString(e)); }
 
+// ---- instrumentation ---------------------------------------------------------------------------
+#include <atomic>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+void pob_count_launch(int n) { g_launches += n; }
+static bool g_timing = false;
+struct TimedSlot {
+  int phase;
+  cudaEvent_t a, b;
+};
+static std::vector<TimedSlot> g_slots;
+static double g_phase_ms[POB_PH_COUNT] = {0, 0, 0, 0, 0};
+static long long g_phase_n[POB_PH_COUNT] = {0, 0, 0, 0, 0};
+PobPhaseTimer::PobPhaseTimer(int phase, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_timing) return;
+  TimedSlot t;
+  t.phase = phase;
+  cudaEventCreate(&t.a);
+  cudaEventCreate(&t.b);
+  cudaEventRecord(t.a, st);
+  g_slots.push_back(t);
+  slot = int(g_slots.size()) - 1;
+}
+PobPhaseTimer::~PobPhaseTimer() {
+  if (slot >= 0) cudaEventRecord(g_slots[slot].b, st);
+}
+static void drain_slots() {
+  for (auto& t : g_slots) {
+    cudaEventSynchronize(t.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      g_phase_ms[t.phase] += ms;
+      g_phase_n[t.phase] += 1;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  g_slots.clear();
+}
+
 namespace {
 
 int fail(const char* where, const char* what) { return pob_fail(where, what); }
@@ -96,6 +136,26 @@ pob::FwdParams pob_base_params(const void* packed, int sh_deg) { return base_par
 extern "C" {
 
 int pob_abi_version(void) { return 1; }
+
+long long pob_launch_count(void) { return g_launches.load(); }
+
+void pob_timing_enable(int on) {
+  drain_slots();
+  g_timing = on != 0;
+  for (int i = 0; i < POB_PH_COUNT; ++i) {
+    g_phase_ms[i] = 0;
+    g_phase_n[i] = 0;
+  }
+}
+
+int pob_timing_read(double* ms_out, long long* launches_out) {
+  drain_slots();
+  for (int i = 0; i < POB_PH_COUNT; ++i) {
+    if (ms_out) ms_out[i] = g_phase_ms[i];
+    if (launches_out) launches_out[i] = g_phase_n[i];
+  }
+  return POB_PH_COUNT;
+}
 const char* pob_last_error(void) { return g_err.c_str(); }
 int pob_sm_count(void) { return sm_count(); }
 
@@ -114,6 +174,8 @@ int pob_pack_weights(const float* flat_dev, int sh_deg, void* packed_dev, void* 
   const int K = K_of(sh_deg);
   const BlobLayout b = blob_layout(K);
   uint8_t* p = static_cast<uint8_t*>(packed_dev);
+  pob_count_launch();
+  PobPhaseTimer _t(POB_PH_OPTIM, (cudaStream_t)stream);
   POB_CUDA("pob_pack_weights",
            pob::launch_pack_weights(flat_dev, K, p + b.w_hi, p + b.w_lo, p + b.wt_hi,
                                     reinterpret_cast<float*>(p + b.bias), (cudaStream_t)stream));
@@ -133,6 +195,8 @@ int pob_eval_points_raw(const void* packed_dev, int sh_deg, const float* points_
   p.out_mode = raw_rgb_dev ? pob::OUT_RAW : pob::OUT_SIGMA;
   p.out_rgb = raw_rgb_dev;
   p.out_sigma = raw_sigma_dev;
+  pob_count_launch();
+  PobPhaseTimer _t(POB_PH_FWD, (cudaStream_t)stream);
   POB_CUDA("pob_eval_points_raw",
            pob::launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sm_count(),
                                (cudaStream_t)stream));
@@ -155,6 +219,8 @@ int pob_eval_points(const void* packed_dev, int sh_deg, const float* points_dev,
   p.viewdirs = viewdirs_dev ? viewdirs_dev : points_dev;
   p.out_mode = pob::OUT_RGBS;
   p.out_rgbs = reinterpret_cast<float4*>(out_rgbs_dev);
+  pob_count_launch();
+  PobPhaseTimer _t(POB_PH_FWD, (cudaStream_t)stream);
   POB_CUDA("pob_eval_points",
            pob::launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sm_count(),
                                (cudaStream_t)stream));
@@ -187,6 +253,8 @@ int pob_eval_grid(const void* packed_dev, int sh_deg, int reso, int x0, int nx, 
   p.out_mode = raw_rgb_dev ? pob::OUT_RAW : pob::OUT_SIGMA;
   p.out_rgb = raw_rgb_dev;
   p.out_sigma = raw_sigma_dev;
+  pob_count_launch();
+  PobPhaseTimer _t(POB_PH_FWD, (cudaStream_t)stream);
   POB_CUDA("pob_eval_grid",
            pob::launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sm_count(),
                                (cudaStream_t)stream));
@@ -233,6 +301,7 @@ int pob_sample_coarse(const float* z_base_dev, const float* t_rand_dev, int n_ra
                       float* z_out_dev, void* stream) {
   if (!z_base_dev || !z_out_dev) return fail("pob_sample_coarse", "NULL pointer");
   if (n_rays < 0 || n_samples < 1) return fail("pob_sample_coarse", "bad sizes");
+  pob_count_launch();
   POB_CUDA("pob_sample_coarse",
            pob::launch_sample_coarse(z_base_dev, t_rand_dev, n_rays, n_samples, z_out_dev, (cudaStream_t)stream));
   return 0;
@@ -243,6 +312,7 @@ int pob_composite(const float* rgbs_dev, const float* z_dev, const float* dirs_d
                   float* out_weights_dev, void* stream) {
   if (!rgbs_dev || !z_dev || !dirs_dev || !out_rgb_dev) return fail("pob_composite", "NULL pointer");
   if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail("pob_composite", "n_samples must be in [1,256]");
+  pob_count_launch();
   POB_CUDA("pob_composite",
            pob::launch_composite_fwd(reinterpret_cast<const float4*>(rgbs_dev), z_dev, dirs_dev, n_rays, n_samples,
                                      white_bkgd, out_rgb_dev, out_disp_dev, out_acc_dev, out_weights_dev,
@@ -256,6 +326,7 @@ int pob_composite_bwd(const float* rgbs_dev, const float* z_dev, const float* di
   if (!rgbs_dev || !z_dev || !dirs_dev || !comp_rgb_dev || !pixels_dev || !g_out_dev)
     return fail("pob_composite_bwd", "NULL pointer");
   if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail("pob_composite_bwd", "n_samples must be in [1,256]");
+  pob_count_launch();
   POB_CUDA("pob_composite_bwd",
            pob::launch_composite_bwd(reinterpret_cast<const float4*>(rgbs_dev), z_dev, dirs_dev, comp_rgb_dev,
                                      pixels_dev, n_rays, n_samples, white_bkgd, gscale,
@@ -268,6 +339,7 @@ int pob_sample_pdf(const float* z_coarse_dev, const float* weights_dev, const fl
   if (!z_coarse_dev || !weights_dev || !u_dev || !z_out_dev) return fail("pob_sample_pdf", "NULL pointer");
   if (n_coarse < 3 || n_fine < 1 || n_coarse + n_fine > 256)
     return fail("pob_sample_pdf", "need n_coarse >= 3 and n_coarse + n_fine <= 256");
+  pob_count_launch();
   POB_CUDA("pob_sample_pdf", pob::launch_sample_pdf(z_coarse_dev, weights_dev, u_dev, u_per_ray, n_rays, n_coarse,
                                                     n_fine, z_out_dev, (cudaStream_t)stream));
   return 0;

@@ -122,7 +122,7 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
   const int sms = pob_sm_count_cached();
   const int Nc = c.num_coarse_samples, Nf = c.num_fine_samples;
   Level& C = w.lv[0];
-  POB_CUDA(where, launch_sample_coarse(z_base, t_rand, R, Nc, C.z, st));
+  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sample_coarse(z_base, t_rand, R, Nc, C.z, st)); }
   {
     FwdParams p = ray_fwd_params(pk_c, c.sh_deg, o, d, v, C.z, R, Nc, C.rgbs);
     if (save) {
@@ -130,25 +130,25 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
       p.save_e = C.E;
       p.save_mask = C.mask;
     }
-    POB_CUDA(where, launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sms, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_FWD, st); POB_CUDA(where, launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sms, st)); }
   }
-  POB_CUDA(where, launch_composite_fwd(C.rgbs, C.z, d, R, Nc, c.white_bkgd, C.comp, C.disp, C.acc, C.weights, st));
+  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_fwd(C.rgbs, C.z, d, R, Nc, c.white_bkgd, C.comp, C.disp, C.acc, C.weights, st)); }
   if (Nf > 0) {
     Level& F = w.lv[1];
     if (z_fine)
       POB_CUDA(where, cudaMemcpyAsync(F.z, z_fine, sizeof(float) * size_t(R) * (Nc + Nf),
                                       cudaMemcpyDeviceToDevice, st));
     else
-      POB_CUDA(where, launch_sample_pdf(C.z, C.weights, u, u_per_ray, R, Nc, Nf, F.z, st));
+      { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sample_pdf(C.z, C.weights, u, u_per_ray, R, Nc, Nf, F.z, st)); }
     FwdParams p = ray_fwd_params(pk_f, c.sh_deg, o, d, v, F.z, R, Nc + Nf, F.rgbs);
     if (save) {
       p.save_h = F.H;
       p.save_e = F.E;
       p.save_mask = F.mask;
     }
-    POB_CUDA(where, launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sms, st));
-    POB_CUDA(where, launch_composite_fwd(F.rgbs, F.z, d, R, Nc + Nf, c.white_bkgd, F.comp, F.disp, F.acc,
-                                         F.weights, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_FWD, st); POB_CUDA(where, launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sms, st)); }
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_fwd(F.rgbs, F.z, d, R, Nc + Nf, c.white_bkgd, F.comp, F.disp, F.acc,
+                                         F.weights, st)); }
   }
   return 0;
 }
@@ -193,6 +193,7 @@ int pob_render_rays(const pob_render_config* cfg, const void* packed_coarse_dev,
                              precision, false, st))
     return e;
   const unsigned grid = (n_rays + 255) / 256;
+  pob_count_launch(cfg->num_fine_samples > 0 ? 2 : 1);
   pack_outputs_kernel<<<grid, 256, 0, st>>>(w.lv[0].comp, w.lv[0].disp, w.lv[0].acc, n_rays, out_coarse_dev);
   if (cfg->num_fine_samples > 0)
     pack_outputs_kernel<<<grid, 256, 0, st>>>(w.lv[1].comp, w.lv[1].disp, w.lv[1].acc, n_rays, out_fine_dev);
@@ -236,11 +237,11 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
   Level& S = w.lv[2];
   const void* pk_main = Nf > 0 ? packed_fine_dev : packed_coarse_dev;  // MLP used by eval_points_raw
   // ---- upstream gradients ----
-  POB_CUDA(where, launch_composite_bwd(C.rgbs, C.z, directions_dev, C.comp, pixels_dev, n_rays, Nc,
-                                       cfg->white_bkgd, gscale, C.G, stats_dev + (Nf > 0 ? 1 : 0), st));
+  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_bwd(C.rgbs, C.z, directions_dev, C.comp, pixels_dev, n_rays, Nc,
+                                       cfg->white_bkgd, gscale, C.G, stats_dev + (Nf > 0 ? 1 : 0), st)); }
   if (Nf > 0)
-    POB_CUDA(where, launch_composite_bwd(F.rgbs, F.z, directions_dev, F.comp, pixels_dev, n_rays, Nc + Nf,
-                                         cfg->white_bkgd, gscale, F.G, stats_dev + 0, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_bwd(F.rgbs, F.z, directions_dev, F.comp, pixels_dev, n_rays, Nc + Nf,
+                                         cfg->white_bkgd, gscale, F.G, stats_dev + 0, st)); }
   long long sp_n = 0;
   if (sparsity) {
     sp_n = cfg->sparsity_npoints;
@@ -253,9 +254,9 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     p.save_h = S.H;
     p.save_e = S.E;
     p.save_mask = S.mask;
-    POB_CUDA(where, launch_mlp_fwd(p, POB_PREC_FP16, false, sms, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_FWD, st); POB_CUDA(where, launch_mlp_fwd(p, POB_PREC_FP16, false, sms, st)); }
     const float coef = hp->loss_scale * hp->sparsity_weight * hp->sparsity_length / float(sp_n);
-    POB_CUDA(where, launch_sparsity_grad(S.sigma, int(sp_n), hp->sparsity_length, coef, S.G, stats_dev + 2, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sparsity_grad(S.sigma, int(sp_n), hp->sparsity_length, coef, S.G, stats_dev + 2, st)); }
   }
   // ---- dgrad chains ----
   auto bwd = [&](const void* pk, Level& L, long long M, const float* vd, int npr) -> cudaError_t {
@@ -273,6 +274,8 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     b.mask = L.mask;
     b.save_dz = L.DZ;
     b.save_do = L.DO;
+    pob_count_launch();
+    PobPhaseTimer _t(POB_PH_BWD, st);
     return launch_mlp_bwd(b, sms, st);
   };
   POB_CUDA(where, bwd(packed_coarse_dev, C, (long long)n_rays * Nc, viewdirs_dev, Nc));
@@ -296,9 +299,9 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     g.partials = w.partials[mlp];
     int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];
     const int nctas = wgrad_assign_roles(g, sms, rs, rc);
-    POB_CUDA(where, launch_mlp_wgrad(g, nctas, st));
-    POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
-                                        grad_flat_dev + size_t(mlp) * P, st));
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_WGRAD, st); POB_CUDA(where, launch_mlp_wgrad(g, nctas, st)); }
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
+                                        grad_flat_dev + size_t(mlp) * P, st)); }
   }
   return 0;
 }
@@ -314,8 +317,8 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
   cudaStream_t st = (cudaStream_t)stream;
   const int K = sh_deg < 0 ? 1 : (sh_deg + 1) * (sh_deg + 1);
   const long long P = flat_layout(K).total;
-  POB_CUDA(where, launch_adam(params_dev, grads_dev, m_dev, v_dev, P * num_mlps, lr, step, 0.9f, 0.999f, 1e-8f,
-                              grad_mult, weight_decay_coef, st));
+  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_adam(params_dev, grads_dev, m_dev, v_dev, P * num_mlps, lr, step, 0.9f, 0.999f, 1e-8f,
+                              grad_mult, weight_decay_coef, st)); }
   if (int e = pob_pack_weights(params_dev, sh_deg, packed_coarse_dev, stream)) return e;
   if (num_mlps == 2)
     if (int e = pob_pack_weights(params_dev + P, sh_deg, packed_fine_dev, stream)) return e;

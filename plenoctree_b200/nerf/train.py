@@ -99,6 +99,23 @@ def stats_from_raw(raw, n_rays, sparsity_weight, sparsity_npoints, two_level, wo
     return Stats(loss, psnr, loss_c, loss_sp, psnr_c, float("nan"))
 
 
+def allreduce_gradients(gbuf):
+    """lax.pmean(grad) + lax.pmean(stats) (nerf_sh/train.py:117-118) as ONE all-reduce(SUM) on the flat
+    [grads | stats] buffer; returns the world size whose reciprocal the caller folds into Adam / stats."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
+        return dist.get_world_size()
+    return 1
+
+
+def shard_batch(batch_size, rank, world):
+    """reference semantics: batch_size is global and split evenly over devices (utils.py:518-522,252)."""
+    if batch_size % world != 0:
+        raise ValueError("Batch size must be divisible by the number of devices.")
+    per = batch_size // world
+    return rank * per, (rank + 1) * per
+
+
 def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
                weight_decay_mult=0.0, randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None,
                sync_stats=False):
@@ -106,10 +123,7 @@ def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.
     device->host read of the six scalars, like the reference's periodic logging), else None."""
     n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand, u,
                       sp_points, loss_scale)
-    world = 1
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        world = dist.get_world_size()
-        dist.all_reduce(state.gbuf, op=dist.ReduceOp.SUM)   # pmean(grad) and pmean(stats) in one bucket
+    world = allreduce_gradients(state.gbuf)   # pmean(grad) and pmean(stats) in one bucket
     # weight_l2 = sum(theta^2)/numel  ->  d/dtheta = 2*theta/numel  (train.py:101-108,114)
     wd = 2.0 * weight_decay_mult / model.params.numel() if weight_decay_mult else 0.0
     check(lib.pob_adam_update(model.sh_deg, model.num_mlps, ptr(model.params), ptr(state.grads), ptr(state.m),

@@ -89,3 +89,10 @@ def umma_probe(a_img, b_img, b_off, adesc, bdesc, dcol, accum, idesc, out_cols):
                              ptr(ac), len(adesc), idesc, out_cols, ptr(out), stream_ptr()))
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+def grid_slab(reso, rank, world):
+    """x-slab [x0, x0+nx) of the extraction grid owned by `rank` (voxel slabs, no collective)."""
+    base, rem = divmod(reso, world)
+    x0 = rank * base + min(rank, rem)
+    return x0, base + (1 if rank < rem else 0)
