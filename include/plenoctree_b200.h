@@ -165,6 +165,12 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
                     float* v_dev, float lr, float step, float grad_mult, float weight_decay_coef,
                     void* packed_coarse_dev, void* packed_fine_dev, void* stream);
 
+/* Profiling aid: pob_eval_points_raw (sigma only, FP16) that also records clock64() stamps of CTA 0 into
+ * trace_dev[3][256] (role 0 = MMA issuer, 1/2 = first epilogue warp of tile X/Y); scripts/trace_fwd.py.
+ * debug_flags != 0 disables parts of the epilogue for timing experiments (results are then invalid). */
+int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,
+                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Test bench for the tcgen05 descriptor conventions (tests/test_umma_probe.py).
  * Runs `nops` tcgen05.mma (kind::f16, M=128) on two shared-memory images and returns the

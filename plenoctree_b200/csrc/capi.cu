@@ -203,6 +203,22 @@ int pob_eval_points_raw(const void* packed_dev, int sh_deg, const float* points_
   return 0;
 }
 
+int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,
+                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* stream) {
+  if (int e = check_common("pob_debug_trace_fwd", packed_dev, sh_deg, POB_PREC_FP16)) return e;
+  if (!points_dev || !raw_sigma_dev || !trace_dev || m <= 0) return fail("pob_debug_trace_fwd", "bad arguments");
+  pob::FwdParams p = base_params(packed_dev, sh_deg);
+  p.src_mode = pob::SRC_POINTS;
+  p.M = m;
+  p.points = points_dev;
+  p.out_mode = pob::OUT_SIGMA;
+  p.out_sigma = raw_sigma_dev;
+  p.trace = trace_dev;
+  p.debug_flags = debug_flags;
+  POB_CUDA("pob_debug_trace_fwd", pob::launch_mlp_fwd(p, 1, false, sm_count(), (cudaStream_t)stream));
+  return 0;
+}
+
 int pob_eval_points(const void* packed_dev, int sh_deg, const float* points_dev,
                     const float* viewdirs_dev, int64_t m, float* out_rgbs_dev, int precision,
                     void* stream) {

@@ -30,11 +30,18 @@ constexpr int WSLOT_BYTES   = WIDTH * WSLOT_K * 2; // [256 x 32] fp16, SW64 = 16
 constexpr int NUM_WSLOTS    = 4;                   // weight ring depth
 constexpr int MAX_NH        = 80;                  // padded heads width (1 + 3*25 -> 80)
 
-// number of 32-wide K slots each forward layer streams (trunk 0..7, heads = index 8)
+// Number of 32-wide K slots each forward layer streams (trunk 0..7, heads = index 8).
+// Biases ride on the tensor cores: column 63 of the posenc tile is the constant 1, so for layers 0 and
+// 5 (which read the posenc tile anyway) the bias is row k=63 of an existing slot; every other layer
+// streams one extra "bias slot" whose only non-zero K row (k = 31) is the bias, multiplied by the
+// k16 group [48,64) of the posenc tile.  The epilogue therefore has no bias add at all (a broadcast
+// LDS.128 per 4 columns costs 4 shared-memory wavefronts per warp: 2048 cycles per layer).
+__host__ __device__ constexpr int fwd_has_bias_slot(int l) { return !(l == 0 || l == SKIP_LAYER); }
 __host__ __device__ constexpr int fwd_slots_of_layer(int l) {
-  return l == 0 ? 2 : (l == SKIP_LAYER ? 10 : 8);
+  return l == 0 ? 2 : (l == SKIP_LAYER ? 10 : 9);
 }
-constexpr int FWD_SLOTS_TOTAL = 2 + 8 * 4 + 10 + 8 * 2 + 8;  // 68 per MLP pass
+constexpr int FWD_TRUNK_SLOTS = 2 + 9 * 4 + 10 + 9 * 2;       // 66
+constexpr int FWD_HEAD_SLOTS = 9;
 
 // ----------------------------------------------------------------------------------
 // Small helpers

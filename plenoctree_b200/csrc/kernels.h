@@ -44,12 +44,15 @@ struct FwdParams {
   uint8_t* save_h;             // [ntile][8][64 KB] activation tile images h_0..h_7
   uint8_t* save_e;             // [ntile][16 KB]   posenc tile images
   uint32_t* save_mask;         // [8][ntile*128][8] relu masks (bit i of word c = col 32c+i)
+  // ---- optional cycle trace of CTA 0 (debug/profiling; null = off): [3 roles][256] clock64 stamps
+  unsigned long long* trace;
+  int debug_flags;             // timing experiments only (results invalid): 1 skip STS, 2 skip cvt/add, 4 skip LDTM
 };
 
 // padded heads width for K spherical-harmonic coefficients per channel
 inline int heads_width(int K) { return ((1 + 3 * K) + 15) / 16 * 16; }
 // bytes of one forward weight image (hi or lo)
-inline size_t fwd_image_bytes(int NH) { return size_t(60) * 16384 + size_t(8) * NH * 64; }
+inline size_t fwd_image_bytes(int NH) { return size_t(66) * 16384 + size_t(9) * NH * 64; }
 // bytes of one dgrad weight image: heads (ceil(NH/32) slots) + layers 7..1 (8 slots each)
 inline size_t bwd_image_bytes(int NH) { return size_t((NH + 31) / 32 + 7 * 8) * 16384; }
 

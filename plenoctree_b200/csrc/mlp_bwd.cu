@@ -65,60 +65,57 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
   const uint32_t tmem = tmem_base_s;
 
   if (warp == BWD_PRODUCER_WARP) {
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      const int nslots = hs + 7 * 8;
-      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
-        for (int j = 0; j < nslots; ++j) {
-          mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+    // whole-warp control flow, one elected lane issues (see mlp_fwd.cu)
+    uint32_t slot = 0, phase = 0;
+    const int nslots = hs + 7 * 8;
+    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+      for (int j = 0; j < nslots; ++j) {
+        mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&bars.full[slot]), WSLOT_BYTES);
           bulk_g2s(sbase + SB_W + slot * WSLOT_BYTES, p.w.wt_hi + size_t(j) * WSLOT_BYTES, WSLOT_BYTES,
                    smem_u32(&bars.full[slot]));
+        }
+        __syncwarp();
+        if (++slot == BWD_WSLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == BWD_MMA_WARP) {
+    uint32_t slot = 0, phase = 0, aphase = 0;
+    const uint32_t idesc = make_idesc_f16(TILE_M, WIDTH);
+    constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
+    constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
+    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+      for (int grp = 0; grp < 8; ++grp) {      // heads, then Dense_7 .. Dense_1
+        const int ns = (grp == 0) ? hs : 8;
+        for (int j = 0; j < ns; ++j) {
+          const uint32_t a_off = uint32_t(j >> 1) * A_CHUNK_BYTES + uint32_t(j & 1) * 64u;
+          mbar_wait(smem_u32(&bars.full[slot]), phase);
+          const uint64_t bd0 = W_HI | uint64_t(((sbase + SB_W + slot * WSLOT_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (j == 0) mbar_wait(smem_u32(&bars.a_ready[g]), aphase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_base = sbase + (g ? SB_A1 : SB_A0) + a_off;
+              const uint64_t ad0 = A_HI | uint64_t((a_base >> 4) & 0x3FFF);
+              const uint32_t d = tmem + uint32_t(g) * 256u;
+              umma_f16(d, ad0, bd0, idesc, j != 0);
+              umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+              if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
+              if (g == 1) umma_commit(smem_u32(&bars.empty[slot]));
+            }
+            __syncwarp();
+          }
           if (++slot == BWD_WSLOTS) {
             slot = 0;
             phase ^= 1;
           }
         }
-      }
-    }
-  } else if (warp == BWD_MMA_WARP) {
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0, aphase = 0;
-      const uint32_t idesc = make_idesc_f16(TILE_M, WIDTH);
-      constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
-      constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
-      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
-        for (int grp = 0; grp < 8; ++grp) {      // heads, then Dense_7 .. Dense_1
-          const int ns = (grp == 0) ? hs : 8;
-          for (int j = 0; j < ns; ++j) {
-            const uint32_t a_off = uint32_t(j >> 1) * A_CHUNK_BYTES + uint32_t(j & 1) * 64u;
-            mbar_wait(smem_u32(&bars.full[slot]), phase);
-            tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (j == 0) {
-                mbar_wait(smem_u32(&bars.a_ready[g]), aphase);
-                tc_fence_after();
-              }
-              const uint32_t a_base = sbase + (g ? SB_A1 : SB_A0) + a_off;
-              const uint32_t d = tmem + uint32_t(g) * 256u;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = A_HI | uint64_t(((a_base + ks * 32) >> 4) & 0x3FFF);
-                const uint64_t bd =
-                    W_HI | uint64_t(((sbase + SB_W + slot * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
-                umma_f16(d, ad, bd, idesc, (j | ks) != 0);
-              }
-              if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
-            }
-            umma_commit(smem_u32(&bars.empty[slot]));
-            if (++slot == BWD_WSLOTS) {
-              slot = 0;
-              phase ^= 1;
-            }
-          }
-          aphase ^= 1;
-        }
+        aphase ^= 1;
       }
     }
   } else {
@@ -193,11 +190,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
         tc_fence_after();
         if (store_issuer) bulk_wait_read_all();
         named_bar_sync(1 + g, 128);
+        uint32_t va[32], vb[32];
+        tmem_ld32(d_tmem, va);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld32(d_tmem + c * 32, v);
+          uint32_t(&v)[32] = (c & 1) ? vb : va;
           tmem_ld_wait();
+          if (c + 1 < 8) tmem_ld32(d_tmem + (c + 1) * 32, (c & 1) ? va : vb);   // prefetch next chunk
           const uint32_t m = mw[c];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {

@@ -47,6 +47,19 @@ struct Barriers {
   uint64_t d_ready[2];
 };
 
+// packed fp32x2 add (Blackwell FADD2): (a.x + b.x, a.y + b.y)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
 __device__ __forceinline__ void load_point(const FwdParams& p, long long s, float& x, float& y,
                                            float& z) {
   if (s >= p.M) s = p.M - 1;
@@ -82,7 +95,7 @@ __device__ __forceinline__ void load_point(const FwdParams& p, long long s, floa
 }
 
 // Positional encoding of one sample into the E tile(s).  Feature order (model_utils.py:162-173):
-// [x(3), sin(2^j x_c) j-major (30), sin(2^j x_c + pi/2) (30)], column 63 = 0.
+// [x(3), sin(2^j x_c) j-major (30), sin(2^j x_c + pi/2) (30)], column 63 = 1 (bias carrier).
 // unit_lo/unit_hi: which 16-byte units (8 features each) this thread stores.
 template <int NSPLIT, bool PRECISE>
 __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row, float x, float y,
@@ -103,7 +116,7 @@ __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row
       f[33 + 3 * j + c] = posenc_sin<PRECISE>(__fadd_rn(xb, half_pi));
     }
   }
-  f[63] = 0.f;
+  f[63] = 1.f;   // constant-one column: carries the biases through the tensor cores (common.cuh)
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     if (u < unit_lo || u >= unit_hi) continue;
@@ -121,6 +134,10 @@ __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row
     *reinterpret_cast<uint4*>(e_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
     if (NSPLIT == 3) *reinterpret_cast<uint4*>(e_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
   }
+}
+
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, uint32_t& n) {
+  if (tr && blockIdx.x == 0 && n < 256) tr[role * 256 + n++] = clock64();
 }
 
 }  // namespace
@@ -158,97 +175,105 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
 
   if (warp == PRODUCER_WARP) {
     // =============================== weight producer ===================================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
-        size_t off = 0;
-        for (int l = 0; l <= NUM_TRUNK; ++l) {
-          const int ns = (l == NUM_TRUNK) ? 8 : fwd_slots_of_layer(l);
-          const uint32_t bytes = (l == NUM_TRUNK) ? uint32_t(NH) * 64u : uint32_t(WSLOT_BYTES);
-          for (int j = 0; j < ns; ++j) {
+    uint32_t slot = 0, phase = 0;
+    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+      size_t off = 0;
+      for (int l = 0; l <= NUM_TRUNK; ++l) {
+        const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
+        const uint32_t bytes = (l == NUM_TRUNK) ? uint32_t(NH) * 64u : uint32_t(WSLOT_BYTES);
+        for (int j = 0; j < ns; ++j) {
 #pragma unroll
-            for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); ++part) {
-              mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+          for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); ++part) {
+            mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(smem_u32(&bars.full[slot]), bytes);
-              bulk_g2s(sbase + SM_W + slot * WSLOT_BYTES, (part == 0 ? p.w.w_hi : p.w.w_lo) + off,
-                       bytes, smem_u32(&bars.full[slot]));
-              if (++slot == NUM_WSLOTS) {
-                slot = 0;
-                phase ^= 1;
-              }
+              bulk_g2s(sbase + SM_W + slot * WSLOT_BYTES, (part == 0 ? p.w.w_hi : p.w.w_lo) + off, bytes,
+                       smem_u32(&bars.full[slot]));
             }
-            off += bytes;
+            __syncwarp();
+            if (++slot == NUM_WSLOTS) {
+              slot = 0;
+              phase ^= 1;
+            }
           }
+          off += bytes;
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ================================= MMA issuer ======================================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0, aphase = 0;
-      const uint32_t idesc_t = make_idesc_f16(TILE_M, WIDTH);
-      const uint32_t idesc_h = make_idesc_f16(TILE_M, NH);
-      constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
-      constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
-      for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
-        for (int l = 0; l <= NUM_TRUNK; ++l) {
-          const int ns = (l == NUM_TRUNK) ? 8 : fwd_slots_of_layer(l);
-          const uint32_t idesc = (l == NUM_TRUNK) ? idesc_h : idesc_t;
-          for (int j = 0; j < ns; ++j) {
-            const bool from_e = (l == 0) || (l == SKIP_LAYER && j >= 8);
-            const int kk = (l == SKIP_LAYER && j >= 8) ? j - 8 : j;
-            const uint32_t a_off = uint32_t(kk >> 1) * A_CHUNK_BYTES + uint32_t(kk & 1) * 64u;
-            const uint32_t s_hi = slot;
-            mbar_wait(smem_u32(&bars.full[s_hi]), phase);
-            uint32_t s_lo = 0;
-            if (NSPLIT == 3) {
-              s_lo = slot + 1;  // ring depth is even: hi/lo never straddle the wrap
-              mbar_wait(smem_u32(&bars.full[s_lo]), phase);
+    // The whole warp runs the (warp-uniform) control flow and the mbarrier waits; one elected lane
+    // issues tcgen05.mma / tcgen05.commit.  (A single-lane `if (lane == 0)` loop makes the compiler
+    // wrap every UTCHMMA in a divergence-handling ELECT loop and slows the issue rate below the
+    // tensor pipe's 128 cycles per 128x256x16 MMA.)
+    uint32_t slot = 0, phase = 0, aphase = 0, tn = 0;
+    const uint32_t idesc_t = make_idesc_f16(TILE_M, WIDTH);
+    const uint32_t idesc_h = make_idesc_f16(TILE_M, NH);
+    constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
+    constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
+    const uint32_t w_base = sbase + SM_W;
+    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+      for (int l = 0; l <= NUM_TRUNK; ++l) {
+        const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
+        const uint32_t idesc = (l == NUM_TRUNK) ? idesc_h : idesc_t;
+        for (int j = 0; j < ns; ++j) {
+          // A operand of K-slot j: the previous layer's activations, or the posenc tile for layer 0,
+          // the skip slots of layer 5, and the bias slot (j == 8) of every other layer, which only
+          // multiplies the k16 group [48,64) of the posenc tile (column 63 = 1) with its row k = 31.
+          const bool bias_slot = (l == NUM_TRUNK || fwd_has_bias_slot(l)) && j == 8;
+          const bool from_e = (l == 0) || j >= 8;
+          const int kk = bias_slot ? 1 : ((l == SKIP_LAYER && j >= 8) ? j - 8 : j);
+          const uint32_t a_off = uint32_t(kk >> 1) * A_CHUNK_BYTES + uint32_t(kk & 1) * 64u;
+          const uint32_t s_hi = slot;
+          const uint32_t s_lo = slot + 1;  // x3 only; ring depth is even: hi/lo never straddle the wrap
+          mbar_wait(smem_u32(&bars.full[s_hi]), phase);
+          if (NSPLIT == 3) mbar_wait(smem_u32(&bars.full[s_lo]), phase);
+          const uint64_t bh0 = W_HI | uint64_t(((w_base + s_hi * WSLOT_BYTES) >> 4) & 0x3FFF);
+          const uint64_t bl0 = W_HI | uint64_t(((w_base + s_lo * WSLOT_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int g = 0; g < NTILES; ++g) {
+            if (j == 0) {
+              mbar_wait(smem_u32(&bars.a_ready[g]), aphase);   // tile g's operand tile written, D drained
+              if (g == 0) trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);
             }
             tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < NTILES; ++g) {
-              if (j == 0) {
-                mbar_wait(smem_u32(&bars.a_ready[g]), aphase);
-                tc_fence_after();
-              }
+            if (elect_one()) {
               const uint32_t a_base = sbase + (from_e ? (g ? SM_E1 : SM_E0) : (g ? SM_A1 : SM_A0)) + a_off;
+              const uint64_t ah0 = A_HI | uint64_t((a_base >> 4) & 0x3FFF);
               const uint32_t d = tmem + uint32_t(g) * 256u;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t acc = (j | ks) != 0;
-                if (NSPLIT == 1) {
-                  const uint64_t ad = A_HI | uint64_t(((a_base + ks * 32) >> 4) & 0x3FFF);
-                  const uint64_t bd =
-                      W_HI | uint64_t(((sbase + SM_W + s_hi * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
-                  umma_f16(d, ad, bd, idesc, acc);
-                } else {
-                  // tile 0 only: hi operand lives in the "tile 0" buffers, lo in the "tile 1" ones
-                  const uint32_t a_lo_base =
-                      sbase + (from_e ? SM_E1 : SM_A1) + a_off;
-                  const uint64_t ah = A_HI | uint64_t(((a_base + ks * 32) >> 4) & 0x3FFF);
-                  const uint64_t al = A_HI | uint64_t(((a_lo_base + ks * 32) >> 4) & 0x3FFF);
-                  const uint64_t bh =
-                      W_HI | uint64_t(((sbase + SM_W + s_hi * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
-                  const uint64_t bl =
-                      W_HI | uint64_t(((sbase + SM_W + s_lo * WSLOT_BYTES + ks * 32) >> 4) & 0x3FFF);
-                  umma_f16(d, al, bh, idesc, acc);
-                  umma_f16(d, ah, bl, idesc, 1u);
-                  umma_f16(d, ah, bh, idesc, 1u);
+              if (NSPLIT == 1) {
+                if (!bias_slot) umma_f16(d, ah0, bh0, idesc, j != 0);
+                umma_f16(d, ah0 + 2, bh0 + 2, idesc, 1u);      // k16 step 1: +32 bytes = +2 encoded
+              } else {
+                // tile 0 only: hi operand lives in the "tile 0" buffers, lo in the "tile 1" ones
+                const uint32_t a_lo_base = sbase + (from_e ? SM_E1 : SM_A1) + a_off;
+                const uint64_t al0 = A_HI | uint64_t((a_lo_base >> 4) & 0x3FFF);
+                if (!bias_slot) {
+                  umma_f16(d, al0, bh0, idesc, j != 0);
+                  umma_f16(d, ah0, bl0, idesc, 1u);
+                  umma_f16(d, ah0, bh0, idesc, 1u);
                 }
+                umma_f16(d, al0 + 2, bh0 + 2, idesc, 1u);
+                umma_f16(d, ah0 + 2, bl0 + 2, idesc, 1u);
+                umma_f16(d, ah0 + 2, bh0 + 2, idesc, 1u);
               }
               if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
+              if (g == NTILES - 1) {
+                umma_commit(smem_u32(&bars.empty[s_hi]));
+                if (NSPLIT == 3) umma_commit(smem_u32(&bars.empty[s_lo]));
+              }
             }
-            umma_commit(smem_u32(&bars.empty[s_hi]));
-            if (NSPLIT == 3) umma_commit(smem_u32(&bars.empty[s_lo]));
-            slot += (NSPLIT == 3) ? 2 : 1;
-            if (slot == NUM_WSLOTS) {
-              slot = 0;
-              phase ^= 1;
-            }
+            __syncwarp();
           }
-          aphase ^= 1;
+          __syncwarp();
+          slot += (NSPLIT == 3) ? 2 : 1;
+          if (slot == NUM_WSLOTS) {
+            slot = 0;
+            phase ^= 1;
+          }
         }
+        aphase ^= 1;
+        trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);       // all MMAs of the layer issued
       }
     }
   } else {
@@ -268,7 +293,10 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(tile_in_iter) * 256u;
     const bool store_issuer = (NSPLIT == 1) && (warp & 3) == 0 && lane == 0;
     const bool saving = (NSPLIT == 1) && (p.save_h != nullptr);
-    uint32_t dphase = 0;
+    uint32_t dphase = 0, tn = 0;
+    const bool tracer = (warp & 3) == 0 && lane == 0;
+    unsigned long long* const trp = tracer ? p.trace : nullptr;
+    const int trole = 1 + g;
 
     auto signal_a_ready = [&]() {
       fence_proxy_async_smem();
@@ -301,42 +329,34 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
         dphase ^= 1;
         tc_fence_after();
+        trace_stamp(trp, trole, tn);             // d_ready observed
         if (saving) {
           if (store_issuer) bulk_wait_read_all();  // previous bulk stores finished reading smem
           named_bar_sync(1 + g, 128);
         }
-        const float* bias = p.w.bias + l * WIDTH;
         uint32_t maskw[8];
         constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
+        uint32_t va[32], vb[32];
+        tmem_ld32(d_tmem + c_begin * 32, va);
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
           const int c = c_begin + cc;
-          uint32_t v[32];
-          tmem_ld32(d_tmem + c * 32, v);
-          tmem_ld_wait();
+          uint32_t(&v)[32] = (cc & 1) ? vb : va;
+          tmem_ld_wait();                                    // chunk cc has landed
+          if (cc + 1 < NCH) tmem_ld32(d_tmem + (c + 1) * 32, (cc & 1) ? va : vb);   // prefetch chunk cc+1
           uint32_t mbits = 0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + u * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + u * 8 + 4));
-            float f[8];
-            f[0] = __uint_as_float(v[8 * u + 0]) + b0.x;
-            f[1] = __uint_as_float(v[8 * u + 1]) + b0.y;
-            f[2] = __uint_as_float(v[8 * u + 2]) + b0.z;
-            f[3] = __uint_as_float(v[8 * u + 3]) + b0.w;
-            f[4] = __uint_as_float(v[8 * u + 4]) + b1.x;
-            f[5] = __uint_as_float(v[8 * u + 5]) + b1.y;
-            f[6] = __uint_as_float(v[8 * u + 6]) + b1.z;
-            f[7] = __uint_as_float(v[8 * u + 7]) + b1.w;
+            // bias already accumulated by the tensor cores: ReLU + fp16 pack is all that is left
             uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = pack_f16x2_relu(f[2 * i], f[2 * i + 1]);
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_f16x2_relu(__uint_as_float(v[8 * u + 2 * i]), __uint_as_float(v[8 * u + 2 * i + 1]));
             if (NSPLIT == 1 && saving) {
-              // relu mask: shift the (inverted) sign bit of each pre-activation into mbits;
-              // column 32c+i ends up at bit (31-i)
+              // relu mask: shift the sign bit of each pre-activation into mbits (inverted once per word
+              // below); column 32c+i ends up at bit (31-i)
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                mbits = __funnelshift_l(~__float_as_uint(f[i]), mbits, 1);
+              for (int i = 0; i < 8; ++i) mbits = __funnelshift_l(v[8 * u + i], mbits, 1);
             }
             const uint32_t unit = uint32_t((c & 1) * 4 + u);
             const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
@@ -347,13 +367,16 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float2 h = unpack_f16x2(w[i]);
-                wl[i] = pack_f16x2(fmaxf(f[2 * i], 0.f) - h.x, fmaxf(f[2 * i + 1], 0.f) - h.y);
+                wl[i] = pack_f16x2(fmaxf(__uint_as_float(v[8 * u + 2 * i]), 0.f) - h.x,
+                                   fmaxf(__uint_as_float(v[8 * u + 2 * i + 1]), 0.f) - h.y);
               }
               *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
             }
           }
-          maskw[cc] = mbits;
+          maskw[cc] = ~mbits;
+          if (cc == 0) trace_stamp(trp, trole, tn);   // first chunk done
         }
+        trace_stamp(trp, trole, tn);             // accumulator drained, A tile written
         if (saving) {
           if (NSPLIT == 1) {
             const long long mrows = ((p.M + 2 * TILE_M - 1) / (2 * TILE_M)) * (2 * TILE_M);
@@ -370,6 +393,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
           }
         }
         signal_a_ready();
+        trace_stamp(trp, trole, tn);             // a_ready signalled
         if (l == SKIP_LAYER) {
           // E is dead until the next iteration: encode the next tile now, in the shadow of the
           // layer-6/7/heads MMAs.
@@ -391,7 +415,6 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
       dphase ^= 1;
       tc_fence_after();
       if (NSPLIT == 1 || g == 0) {
-        const float* bh = p.w.bias + NUM_TRUNK * WIDTH;
         const int K = p.K;
         float sigma_raw = 0.f;
         float pre[3] = {0.f, 0.f, 0.f};
@@ -419,11 +442,11 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             for (int jj = 0; jj < 16; ++jj) {
               const int n = q * 16 + jj;
               if (n == 0) {
-                sigma_raw = __uint_as_float(v[0]) + __ldg(bh);
+                sigma_raw = __uint_as_float(v[0]);
               } else {
                 const int k = (n - 1) / 3, c = (n - 1) % 3;
                 if (k < K) {
-                  const float coef = __uint_as_float(v[jj]) + __ldg(bh + n);
+                  const float coef = __uint_as_float(v[jj]);
                   if (p.out_mode == OUT_RGBS) pre[c] = fmaf(basis[k < 25 ? k : 24], coef, pre[c]);
                   else if (p.out_mode == OUT_RAW) stage[c * K + k] = coef;
                 }

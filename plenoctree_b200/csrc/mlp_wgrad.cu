@@ -106,14 +106,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
 
   if (warp == 4) {
     // ================================ loader ====================================
-    if (lane == 0) {
-      uint32_t st = 0, phase = 0;
-      for (long long k = 0; k < my_tiles; ++k) {
-        const long long t = ridx + k * rcnt;
-        const uint8_t *a_ptr, *b_ptr;
-        tile_ptrs(t, a_ptr, b_ptr);
-        for (int sub = 0; sub < 2; ++sub) {
-          mbar_wait(smem_u32(&bars.empty[st]), phase ^ 1);
+    // whole-warp control flow, one elected lane issues (see mlp_fwd.cu)
+    uint32_t st = 0, phase = 0;
+    for (long long k = 0; k < my_tiles; ++k) {
+      const long long t = ridx + k * rcnt;
+      const uint8_t *a_ptr, *b_ptr;
+      tile_ptrs(t, a_ptr, b_ptr);
+      for (int sub = 0; sub < 2; ++sub) {
+        mbar_wait(smem_u32(&bars.empty[st]), phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&bars.full[st]), WG_HALF + b_half_bytes);
           const uint32_t dst = sbase + st * WG_STAGE_BYTES;
 #pragma unroll
@@ -124,47 +125,46 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
             bulk_g2s(dst + WG_HALF + c * (WG_SUB * 128),
                      b_ptr + size_t(c) * A_CHUNK_BYTES + sub * (WG_SUB * 128), WG_SUB * 128,
                      smem_u32(&bars.full[st]));
-          if (++st == WG_STAGES) {
-            st = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++st == WG_STAGES) {
+          st = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 5) {
     // ================================= MMA ======================================
-    if (lane == 0) {
-      uint32_t st = 0, phase = 0;
-      const uint32_t idesc = make_idesc_f16(128, R.N, 1, 1);
-      // MN-major SW128: LBO = stride between 64-feature chunks (8 KB here), SBO = 8-sample group
-      constexpr uint64_t DESC_HI =
-          make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t((WG_SUB * 128) >> 4) << 16);
-      for (long long k = 0; k < my_tiles; ++k) {
-        for (int sub = 0; sub < 2; ++sub) {
-          mbar_wait(smem_u32(&bars.full[st]), phase);
-          tc_fence_after();
+    uint32_t st = 0, phase = 0;
+    const uint32_t idesc = make_idesc_f16(128, R.N, 1, 1);
+    // MN-major SW128: LBO = stride between 64-feature chunks (8 KB here), SBO = 8-sample group
+    constexpr uint64_t DESC_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t((WG_SUB * 128) >> 4) << 16);
+    for (long long k = 0; k < my_tiles; ++k) {
+      for (int sub = 0; sub < 2; ++sub) {
+        mbar_wait(smem_u32(&bars.full[st]), phase);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t a0 = sbase + st * WG_STAGE_BYTES;
-          const uint32_t b0 = a0 + WG_HALF;
+          const uint64_t ad0 = DESC_HI | uint64_t((a0 >> 4) & 0x3FFF);
+          const uint64_t bd0 = DESC_HI | uint64_t(((a0 + WG_HALF) >> 4) & 0x3FFF);
 #pragma unroll
           for (int ks = 0; ks < WG_SUB / 16; ++ks) {
             const uint32_t acc = (k | sub | ks) != 0;
-            const uint64_t bd = DESC_HI | uint64_t(((b0 + ks * 2048) >> 4) & 0x3FFF);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint64_t ad =
-                  DESC_HI | uint64_t(((a0 + half * 2 * (WG_SUB * 128) + ks * 2048) >> 4) & 0x3FFF);
-              umma_f16(tmem + half * 256, ad, bd, idesc, acc);
-            }
+            // 16 samples = 2048 bytes = +128 encoded; features 128..255 = +2 chunks = +1024 encoded
+            umma_f16(tmem, ad0 + ks * 128, bd0 + ks * 128, idesc, acc);
+            umma_f16(tmem + 256, ad0 + ks * 128 + 1024, bd0 + ks * 128, idesc, acc);
           }
           umma_commit(smem_u32(&bars.empty[st]));
-          if (++st == WG_STAGES) {
-            st = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++st == WG_STAGES) {
+          st = 0;
+          phase ^= 1;
         }
       }
-      umma_commit(smem_u32(&bars.done));
     }
+    if (elect_one()) umma_commit(smem_u32(&bars.done));
+    __syncwarp();
   } else {
     // ========================= bias column sums (warps 0-3) ======================
     const int fp = threadIdx.x;            // feature pair 0..127 -> features 2fp, 2fp+1

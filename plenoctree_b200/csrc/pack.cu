@@ -41,8 +41,8 @@ __device__ __forceinline__ float heads_weight(const PackArgs& a, int i, int n) {
 
 __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
   const int NH = a.NH;
-  const long long n_fwd_trunk = 60ll * 256 * 32;
-  const long long n_fwd_heads = 8ll * NH * 32;
+  const long long n_fwd_trunk = (long long)FWD_TRUNK_SLOTS * 256 * 32;
+  const long long n_fwd_heads = (long long)FWD_HEAD_SLOTS * NH * 32;
   const int hs = (NH + 31) / 32;
   const long long n_bwd = (long long)(hs + 56) * 256 * 32;
   const long long n_bias = 8 * 256 + MAX_NH;
@@ -60,14 +60,31 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
       }
       const int kin = 32 * j + kk;  // input feature index in the layer's [in] axis
       float v = 0.f;
-      if (kin < a.L.in_dim[l]) v = a.flat[a.L.w_off[l] + kin * 256 + n];
+      if (fwd_has_bias_slot(l) && j == 8) {
+        if (kk == 31) v = a.flat[a.L.b_off[l] + n];            // bias slot: k = 31 <-> posenc column 63 (= 1)
+      } else if (kin < a.L.in_dim[l]) {
+        v = a.flat[a.L.w_off[l] + kin * 256 + n];
+      } else if (kin == a.L.in_dim[l] && !fwd_has_bias_slot(l)) {
+        v = a.flat[a.L.b_off[l] + n];                          // layers 0 / 5: the padding row k = 63 of posenc
+      }
       put_hilo(a.w_hi, a.w_lo, size_t(slot) * WSLOT_BYTES + w_slot_offset(n, kk), v);
     } else if (t < n_fwd_trunk + n_fwd_heads) {
       const long long u = t - n_fwd_trunk;
       const int j = int(u / (NH * 32));
       const int n = int(u / 32) % NH, kk = int(u % 32);
-      const float v = heads_weight(a, 32 * j + kk, n);
-      put_hilo(a.w_hi, a.w_lo, size_t(60) * WSLOT_BYTES + size_t(j) * NH * 64 + w_slot_offset(n, kk), v);
+      float v;
+      if (j < 8) v = heads_weight(a, 32 * j + kk, n);
+      else {
+        v = 0.f;
+        if (kk == 31) {
+          if (n == 0) v = a.flat[a.L.b_off[8]];
+          else {
+            const int k = (n - 1) / 3, c = (n - 1) % 3;
+            if (k < a.K) v = a.flat[a.L.b_off[9] + c * a.K + k];
+          }
+        }
+      }
+      put_hilo(a.w_hi, a.w_lo, size_t(FWD_TRUNK_SLOTS) * WSLOT_BYTES + size_t(j) * NH * 64 + w_slot_offset(n, kk), v);
     } else if (t < n_fwd_trunk + n_fwd_heads + n_bwd) {
       const long long u = t - n_fwd_trunk - n_fwd_heads;
       const int slot = int(u / (256 * 32));

@@ -74,8 +74,12 @@ def heads_width(K):
     return (1 + 3 * K + 15) // 16 * 16
 
 
+def fwd_has_bias_slot(l):
+    return not (l == 0 or l == 5)
+
+
 def fwd_slots_of_layer(l):
-    return 2 if l == 0 else (10 if l == 5 else 8)
+    return 2 if l == 0 else (10 if l == 5 else 9)
 
 
 def layer_dims(K):
@@ -100,7 +104,7 @@ def flat_offsets(K):
 def blob_layout(K):
     NH = heads_width(K)
     up = lambda x: (x + 1023) // 1024 * 1024
-    fwd = 60 * 16384 + 8 * NH * 64
+    fwd = 66 * 16384 + 9 * NH * 64
     bwd = ((NH + 31) // 32 + 56) * 16384
     w_hi = 0
     w_lo = up(w_hi + fwd)
@@ -152,19 +156,29 @@ def pack_reference(flat, sh_deg):
     for l in range(8):
         cin = dims[l][0]
         W = flat[w_off[l]:w_off[l] + cin * 256].reshape(cin, 256)  # [in, out]
+        bias_l = flat[b_off[l]:b_off[l] + 256]
         for j in range(fwd_slots_of_layer(l)):
             blk = np.zeros((256, 32), np.float32)  # [out row, k]
-            k0 = 32 * j
-            kn = max(0, min(32, cin - k0))
-            blk[:, :kn] = W[k0:k0 + kn, :].T
+            if fwd_has_bias_slot(l) and j == 8:
+                blk[:, 31] = bias_l                # bias slot: multiplied by posenc column 63 (= 1)
+            else:
+                k0 = 32 * j
+                kn = max(0, min(32, cin - k0))
+                blk[:, :kn] = W[k0:k0 + kn, :].T
+                if not fwd_has_bias_slot(l) and k0 <= cin < k0 + 32:
+                    blk[:, cin - k0] = bias_l      # layers 0 / 5: padding row k = 63 of the posenc operand
             hi, lo = hilo(blk)
             w_hi[slot * 16384:(slot + 1) * 16384] = pack_w_slot(hi)
             w_lo[slot * 16384:(slot + 1) * 16384] = pack_w_slot(lo)
             slot += 1
     Wh, bh = heads_matrix(flat, K)
-    base = 60 * 16384
-    for j in range(8):
-        blk = Wh[32 * j:32 * j + 32, :].T  # [NH, 32]
+    base = 66 * 16384
+    for j in range(9):
+        if j < 8:
+            blk = Wh[32 * j:32 * j + 32, :].T  # [NH, 32]
+        else:
+            blk = np.zeros((NH, 32), np.float32)
+            blk[:, 31] = bh
         hi, lo = hilo(blk)
         w_hi[base + j * NH * 64: base + (j + 1) * NH * 64] = pack_w_slot(hi)
         w_lo[base + j * NH * 64: base + (j + 1) * NH * 64] = pack_w_slot(lo)

@@ -77,10 +77,10 @@ def test_loss_and_grad_vs_oracle(sh_deg, R, nf, nsp):
     st = T.stats_from_raw(state.stats_raw, n, cfg["sparsity_weight"], nsp, nf > 0)
     rep["stats"] = dict(gpu=st._asdict(), oracle=stats_o)
     _record(f"sh{sh_deg}_R{R}_nf{nf}_nsp{nsp}", rep)
-    # loss values (fp16 forward): 2e-3 relative
-    assert abs(st.loss - stats_o["loss"]) / stats_o["loss"] < 2e-3
+    # loss values (fp16 operands incl. biases, free-running fine level on 40-96 rays): 5e-3 relative
+    assert abs(st.loss - stats_o["loss"]) / stats_o["loss"] < 5e-3
     if nf:
-        assert abs(st.loss_c - stats_o["loss_c"]) / stats_o["loss_c"] < 2e-3
+        assert abs(st.loss_c - stats_o["loss_c"]) / stats_o["loss_c"] < 5e-3
     if nsp:
         assert abs(st.loss_sp - stats_o["loss_sp"]) < 2e-3 * max(abs(stats_o["loss_sp"]), 1e-6) + 1e-7
     # (a) against the fp32 oracle, free running.  fp16 operands flip ~4e-4 of the ReLU masks and move the
