@@ -167,9 +167,11 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
 
 /* Profiling aid: pob_eval_points_raw (sigma only, FP16) that also records clock64() stamps of CTA 0 into
  * trace_dev[3][256] (role 0 = MMA issuer, 1/2 = first epilogue warp of tile X/Y); scripts/trace_fwd.py.
- * debug_flags != 0 disables parts of the epilogue for timing experiments (results are then invalid). */
+ * save_*_dev (all or none; sized like the training workspace: 512 KB, 16 KB and 4 KB per 128 samples) turn
+ * on the training-mode stores so their cost shows in the trace. */
 int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,
-                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* stream);
+                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* save_h_dev,
+                        void* save_e_dev, void* save_mask_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Test bench for the tcgen05 descriptor conventions (tests/test_umma_probe.py).

@@ -204,7 +204,8 @@ int pob_eval_points_raw(const void* packed_dev, int sh_deg, const float* points_
 }
 
 int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,
-                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* stream) {
+                        float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* save_h_dev,
+                        void* save_e_dev, void* save_mask_dev, void* stream) {
   if (int e = check_common("pob_debug_trace_fwd", packed_dev, sh_deg, POB_PREC_FP16)) return e;
   if (!points_dev || !raw_sigma_dev || !trace_dev || m <= 0) return fail("pob_debug_trace_fwd", "bad arguments");
   pob::FwdParams p = base_params(packed_dev, sh_deg);
@@ -215,6 +216,9 @@ int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_
   p.out_sigma = raw_sigma_dev;
   p.trace = trace_dev;
   p.debug_flags = debug_flags;
+  p.save_h = static_cast<uint8_t*>(save_h_dev);
+  p.save_e = static_cast<uint8_t*>(save_e_dev);
+  p.save_mask = static_cast<uint32_t*>(save_mask_dev);
   POB_CUDA("pob_debug_trace_fwd", pob::launch_mlp_fwd(p, 1, false, sm_count(), (cudaStream_t)stream));
   return 0;
 }

@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
     const int row = int((warp & 3) * 32 + lane);
     uint8_t* const a_tile = smem + (g ? SB_A1 : SB_A0);
     const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(g) * 256u;
-    const bool store_issuer = (warp & 3) == 0 && lane == 0;
     uint32_t dphase = 0;
 
     for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
@@ -133,6 +132,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
       {
         float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
         float basis[25];
+#pragma unroll
+        for (int k = 0; k < 25; ++k) basis[k] = 0.f;   // padded rows: 0 * garbage must not become NaN
         basis[0] = 1.f;
         if (s < p.M) {
           gq = p.G[s];
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
           if (p.sh_deg >= 0) sh_basis(p.sh_deg, __ldg(vd), __ldg(vd + 1), __ldg(vd + 2), basis);
         }
         const float gc[3] = {gq.x, gq.y, gq.z};
-        if (store_issuer) bulk_wait_read_all();   // previous iteration's dZ_0 store done reading
+        // dO / dZ tiles go to global memory straight from the registers (a bulk store out of shared
+        // memory competes with the MMA operand reads of the next GEMM)
+        uint8_t* const do_glob = p.save_do + size_t(tile_idx) * (2 * A_CHUNK_BYTES);
+        // every warp of the group must be done copying the previous iteration's dZ_0 image out of a_tile
         named_bar_sync(1 + g, 128);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {            // 16-byte units of 8 columns, up to 128 columns
@@ -168,13 +172,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
             *reinterpret_cast<uint4*>(a_tile + off) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
-        if (store_issuer) {
-          bulk_s2g(p.save_do + size_t(tile_idx) * (2 * A_CHUNK_BYTES), smem_u32(a_tile),
-                   uint32_t(do_chunks) * A_CHUNK_BYTES);
-          bulk_commit();
+        {
+          // dO tile -> global, linear coalesced copy of the finished shared-memory image
+          const int t = int(threadIdx.x & 127);
+          const uint4* src = reinterpret_cast<const uint4*>(a_tile) + t;
+          uint4* dst = reinterpret_cast<uint4*>(do_glob) + t;
+          for (int i = 0; i < do_chunks * (A_CHUNK_BYTES / 16 / 128); ++i) dst[i * 128] = src[i * 128];
         }
+        fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars.a_ready[g]));
@@ -188,8 +194,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
         mbar_wait(smem_u32(&bars.d_ready[g]), dphase);
         dphase ^= 1;
         tc_fence_after();
-        if (store_issuer) bulk_wait_read_all();
-        named_bar_sync(1 + g, 128);
+        uint8_t* const dz_glob = p.save_dz + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES;
         uint32_t va[32], vb[32];
         tmem_ld32(d_tmem, va);
 #pragma unroll
@@ -214,13 +219,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
             *reinterpret_cast<uint4*>(a_tile + off) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
-        if (store_issuer) {
-          bulk_s2g(p.save_dz + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES, smem_u32(a_tile),
-                   A_TILE_BYTES);
-          bulk_commit();
+        {
+          // dZ_l tile -> global (see mlp_fwd.cu: copy before the hand-over, not a bulk store after it)
+          const int t = int(threadIdx.x & 127);
+          const uint4* src = reinterpret_cast<const uint4*>(a_tile) + t;
+          uint4* dst = reinterpret_cast<uint4*>(dz_glob) + t;
+#pragma unroll 8
+          for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
         }
+        fence_proxy_async_smem();
         if (l > 0) {
           tc_fence_before();
           __syncwarp();
@@ -228,7 +236,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_bwd_kernel(const __grid_co
         }
       }
     }
-    if (store_issuer) bulk_wait_all();
   }
 
   tc_fence_before();

@@ -99,7 +99,7 @@ __device__ __forceinline__ void load_point(const FwdParams& p, long long s, floa
 // unit_lo/unit_hi: which 16-byte units (8 features each) this thread stores.
 template <int NSPLIT, bool PRECISE>
 __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row, float x, float y,
-                                           float z, int unit_lo, int unit_hi) {
+                                           float z, int unit_lo, int unit_hi, uint8_t* e_glob = nullptr) {
   float f[64];
   f[0] = x;
   f[1] = y;
@@ -133,6 +133,7 @@ __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row
     const uint32_t off = uint32_t(row) * 128u + (uint32_t(u ^ (row & 7)) << 4);
     *reinterpret_cast<uint4*>(e_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
     if (NSPLIT == 3) *reinterpret_cast<uint4*>(e_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    if (e_glob) *reinterpret_cast<uint4*>(e_glob + off) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -291,7 +292,6 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     uint8_t* const e_lo = smem + SM_E1;
     const int unit_lo = (NSPLIT == 1) ? 0 : 4 * g, unit_hi = (NSPLIT == 1) ? 8 : 4 * g + 4;
     const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(tile_in_iter) * 256u;
-    const bool store_issuer = (NSPLIT == 1) && (warp & 3) == 0 && lane == 0;
     const bool saving = (NSPLIT == 1) && (p.save_h != nullptr);
     uint32_t dphase = 0, tn = 0;
     const bool tracer = (warp & 3) == 0 && lane == 0;
@@ -309,31 +309,22 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     if (it < num_iters) {
       float x, y, z;
       load_point(p, it * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
-      posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi);
+      posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi,
+                                  saving ? p.save_e + size_t(it * NTILES + tile_in_iter) * E_TILE_BYTES : nullptr);
       signal_a_ready();
     }
     for (; it < num_iters; it += gridDim.x) {
       const long long tile_idx = it * NTILES + tile_in_iter;
       const long long s = tile_idx * TILE_M + row;
-      if (saving) {
-        // E tile of this iteration is complete (group-wide) once a_ready fired; make sure all 4
-        // warps of the group have written before the bulk store reads it.
-        named_bar_sync(1 + g, 128);
-        if (store_issuer) {
-          bulk_s2g(p.save_e + size_t(tile_idx) * E_TILE_BYTES, smem_u32(e_hi), E_TILE_BYTES);
-          bulk_commit();
-        }
-      }
       // ------------------------------ trunk layers ------------------------------------
       for (int l = 0; l < NUM_TRUNK; ++l) {
         mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
         dphase ^= 1;
         tc_fence_after();
         trace_stamp(trp, trole, tn);             // d_ready observed
-        if (saving) {
-          if (store_issuer) bulk_wait_read_all();  // previous bulk stores finished reading smem
-          named_bar_sync(1 + g, 128);
-        }
+        // training: h_l tiles go to global memory straight from the registers (a bulk store out of
+        // shared memory competes with the next layer's MMA operand reads and halves the MMA rate)
+        uint8_t* const h_glob = saving ? p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES : nullptr;
         uint32_t maskw[8];
         constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
         uint32_t va[32], vb[32];
@@ -384,12 +375,17 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
             mp[1] = make_uint4(maskw[NCH - 4], maskw[NCH - 3], maskw[NCH - 2], maskw[NCH - 1]);
           }
-          fence_proxy_async_smem();
+          // h_l tile -> global: the shared-memory image already has the final layout, so the group's 128
+          // threads copy it linearly (coalesced 512 B per warp instruction) BEFORE the tile is handed to
+          // the MMA warp; a bulk store issued here instead would read shared memory during the next
+          // layer's MMAs and halve their rate (profiles/r1: MMA phase 4.4k -> 9.4k cycles).
           named_bar_sync(1 + g, 128);
-          if (store_issuer) {
-            bulk_s2g(p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES, smem_u32(a_hi),
-                     A_TILE_BYTES);
-            bulk_commit();
+          {
+            const int t = int(threadIdx.x & 127);
+            const uint4* src = reinterpret_cast<const uint4*>(a_hi) + t;
+            uint4* dst = reinterpret_cast<uint4*>(h_glob) + t;
+#pragma unroll 8
+            for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
           }
         }
         signal_a_ready();
@@ -399,13 +395,11 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
           // layer-6/7/heads MMAs.
           const long long nit = it + gridDim.x;
           if (nit < num_iters) {
-            if (saving) {
-              if (store_issuer) bulk_wait_read_all();
-              named_bar_sync(1 + g, 128);
-            }
             float x, y, z;
             load_point(p, nit * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
-            posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi);
+            posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi,
+                                        saving ? p.save_e + size_t(nit * NTILES + tile_in_iter) * E_TILE_BYTES
+                                               : nullptr);
             fence_proxy_async_smem();
           }
         }
@@ -482,7 +476,6 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
       // heads accumulator drained, next E tile already encoded (or this was the last iteration)
       signal_a_ready();
     }
-    if (saving && store_issuer) bulk_wait_all();
   }
 
   tc_fence_before();
