@@ -79,6 +79,12 @@ int pob_eval_grid(const void* packed_dev, int sh_deg, int reso, int x0, int nx, 
                   const float offset[3], const float scale[3], float* raw_rgb_dev,
                   float* raw_sigma_dev, int precision, void* stream);
 
+/* Anti-aliasing pass of octree.extraction step2 (octree/extraction.py:355-394, SH data formats): the caller
+ * provides samples_per_cell points per leaf (tree[inds].sample(S), [n_cells*S, 3], cell-major);
+ * out_dev [n_cells, 3K+1] = mean over the S samples of cat([raw_rgb, raw_sigma], -1)  (:391-393). */
+int pob_eval_cells_mean(const void* packed_dev, int sh_deg, const float* points_dev, int64_t n_cells,
+                        int samples_per_cell, float* out_dev, int precision, void* stream);
+
 /* Host-buffer convenience form of pob_eval_points_raw (H2D, kernel, D2H inside the call);
  * the e2e arm of bench.py times this. */
 int pob_eval_points_raw_host(const void* packed_dev, int sh_deg, const float* points_host,

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pob_eval_points_raw": (_i, [_vp, _i, _fp, _i64, _fp, _fp, _i, _vp]),
     "pob_debug_trace_fwd": (_i, [_vp, _i, _fp, _i64, _fp, _vp, _i, _vp, _vp, _vp, _vp]),
     "pob_eval_points": (_i, [_vp, _i, _fp, _fp, _i64, _fp, _i, _vp]),
+    "pob_eval_cells_mean": (_i, [_vp, _i, _fp, _i64, _i, _fp, _i, _vp]),
     "pob_eval_grid": (_i, [_vp, _i, _i, _i, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
                            _fp, _fp, _i, _vp]),
     "pob_eval_points_raw_host": (_i, [_vp, _i, _fp, _i64, _fp, _fp, _i]),

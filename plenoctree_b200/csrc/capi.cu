@@ -247,6 +247,28 @@ int pob_eval_points(const void* packed_dev, int sh_deg, const float* points_dev,
   return 0;
 }
 
+int pob_eval_cells_mean(const void* packed_dev, int sh_deg, const float* points_dev, int64_t n_cells,
+                        int samples_per_cell, float* out_dev, int precision, void* stream) {
+  if (int e = check_common("pob_eval_cells_mean", packed_dev, sh_deg, precision)) return e;
+  if (n_cells < 0 || samples_per_cell <= 0) return fail("pob_eval_cells_mean", "bad sizes");
+  if (n_cells == 0) return 0;
+  if (!points_dev || !out_dev) return fail("pob_eval_cells_mean", "NULL pointer");
+  pob::FwdParams p = base_params(packed_dev, sh_deg);
+  p.src_mode = pob::SRC_POINTS;
+  p.M = n_cells * (int64_t)samples_per_cell;
+  p.points = points_dev;
+  p.out_mode = pob::OUT_CELL_MEAN;
+  p.out_cell = out_dev;
+  p.cell_S = samples_per_cell;
+  POB_CUDA("pob_eval_cells_mean",
+           cudaMemsetAsync(out_dev, 0, sizeof(float) * n_cells * (3 * p.K + 1), (cudaStream_t)stream));
+  pob_count_launch();
+  PobPhaseTimer _t(POB_PH_FWD, (cudaStream_t)stream);
+  POB_CUDA("pob_eval_cells_mean",
+           pob::launch_mlp_fwd(p, precision, precision == POB_PREC_FP16X3, sm_count(), (cudaStream_t)stream));
+  return 0;
+}
+
 int pob_eval_grid(const void* packed_dev, int sh_deg, int reso, int x0, int nx, int ny, int nz,
                   const float offset[3], const float scale[3], float* raw_rgb_dev,
                   float* raw_sigma_dev, int precision, void* stream) {

@@ -14,7 +14,7 @@ struct MlpPacked {
 };
 
 enum SrcMode : int { SRC_POINTS = 0, SRC_RAYS = 1, SRC_GRID = 2 };
-enum OutMode : int { OUT_RAW = 0, OUT_SIGMA = 1, OUT_RGBS = 2 };
+enum OutMode : int { OUT_RAW = 0, OUT_SIGMA = 1, OUT_RGBS = 2, OUT_CELL_MEAN = 3 };
 
 struct FwdParams {
   // ---- sample source ----
@@ -40,6 +40,8 @@ struct FwdParams {
   float* out_rgb;              // OUT_RAW: [M, 3K] (reference channel-major order c*K+k)
   float* out_sigma;            // OUT_RAW / OUT_SIGMA: [M]
   float4* out_rgbs;            // OUT_RGBS: [M] (sigmoid(rgb), relu(sigma))
+  float* out_cell;             // OUT_CELL_MEAN: [M / cell_S, 3K+1] += mean over the cell's samples of
+  int cell_S;                  //   cat([raw_rgb, raw_sigma]) (octree/extraction.py:391-393); zeroed by caller
   // ---- training saves (fast mode only; null = off) ----
   uint8_t* save_h;             // [ntile][8][64 KB] activation tile images h_0..h_7
   uint8_t* save_e;             // [ntile][16 KB]   posenc tile images

@@ -137,6 +137,21 @@ __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row
   }
 }
 
+// extraction step 2 (octree/extraction.py:367-394): accumulate value/S into out_cell[cell][idx].  When the
+// cell size is a multiple of the warp size all 32 rows of a warp belong to one cell: shuffle-reduce first.
+__device__ __forceinline__ void cell_accumulate(const FwdParams& p, long long s, int idx, float v) {
+  const float inv = 1.0f / float(p.cell_S);
+  const int width = 3 * p.K + 1;
+  if ((p.cell_S & 31) == 0) {
+    v = (s < p.M) ? v : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && s < p.M) atomicAdd(p.out_cell + (s / p.cell_S) * width + idx, v * inv);
+  } else if (s < p.M) {
+    atomicAdd(p.out_cell + (s / p.cell_S) * width + idx, v * inv);
+  }
+}
+
 __device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, uint32_t& n) {
   if (tr && blockIdx.x == 0 && n < 256) tr[role * 256 + n++] = clock64();
 }
@@ -443,6 +458,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
                   const float coef = __uint_as_float(v[jj]);
                   if (p.out_mode == OUT_RGBS) pre[c] = fmaf(basis[k < 25 ? k : 24], coef, pre[c]);
                   else if (p.out_mode == OUT_RAW) stage[c * K + k] = coef;
+                  else if (p.out_mode == OUT_CELL_MEAN) cell_accumulate(p, s, c * K + k, coef);
                 }
               }
             }
@@ -457,6 +473,8 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             o.w = fmaxf(sigma_raw, 0.f);
             p.out_rgbs[s] = o;
           }
+        } else if (p.out_mode == OUT_CELL_MEAN) {
+          cell_accumulate(p, s, 3 * K, sigma_raw);
         } else {
           if (s < p.M) p.out_sigma[s] = sigma_raw;
           if (p.out_mode == OUT_RAW) {

@@ -48,3 +48,62 @@ def random_rays_np(n, seed, w=800, h=800, camera_angle_x=0.6911112070083618, rad
     v = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
     px = rs.uniform(0, 1, size=(n, 3)).astype(np.float32)
     return o, d, v, px
+
+
+def render_image(model, rays, normalize_disp=False, chunk=8192, precision=None):
+    """utils.render_image (nerf_sh/nerf/utils.py:331-381): render all the pixels of an image (test mode,
+    randomized=False) in chunks of `chunk` rays; with torch.distributed initialised every rank renders a
+    contiguous slice of each chunk (reference: shard over devices + all_gather, utils.py:357-371,701-706).
+
+    rays: Rays of [H, W, 3] arrays.  Returns rgb [H,W,3], disp [H,W,1], acc [H,W,1] (torch CUDA tensors)."""
+    import torch
+    import torch.distributed as dist
+    from .models import Rays, _cuda_f32
+
+    height, width = rays.origins.shape[:2]
+    num_rays = height * width
+    flat = Rays(*[_cuda_f32(np.ascontiguousarray(r).reshape(num_rays, -1) if isinstance(r, np.ndarray)
+                            else r.reshape(num_rays, -1), "rays") for r in rays])
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    chunk = min(chunk, model.max_rays * world)
+    out = []
+    for i in range(0, num_rays, chunk):
+        n = min(chunk, num_rays - i)
+        per = (n + world - 1) // world
+        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        part = torch.zeros((per, 5), dtype=torch.float32, device=model.device)
+        if hi > lo:
+            sl = Rays(*[r[i + lo:i + hi] for r in flat])
+            rgb, disp, acc = model(sl, randomized=False, precision=precision)[-1]
+            part[:hi - lo, :3], part[:hi - lo, 3], part[:hi - lo, 4] = rgb, disp, acc
+        if world > 1:
+            full = torch.empty((world * per, 5), dtype=torch.float32, device=model.device)
+            dist.all_gather_into_tensor(full, part)
+            part = full
+        out.append(part[:n])
+    res = torch.cat(out, 0)
+    rgb, disp, acc = res[:, :3], res[:, 3:4], res[:, 4:5]
+    if normalize_disp:   # utils.py:376-378
+        disp = (disp - disp.min()) / (disp.max() - disp.min())
+    return rgb.reshape(height, width, 3), disp.reshape(height, width, 1), acc.reshape(height, width, 1)
+
+
+def eval_points(model, points, chunk=720720, to_cpu=False, coarse=False, precision=None):
+    """utils.eval_points (nerf_sh/nerf/utils.py:282-328): raw SH coefficients and sigma of arbitrary points,
+    evaluated chunk by chunk.  Returns (raw_rgb [M,3K], raw_sigma [M,1])."""
+    import torch
+    from .models import _cuda_f32
+
+    points = _cuda_f32(points, "points", 3)
+    rgbs, sigmas = [], []
+    for i in range(0, points.shape[0], chunk):
+        rgb, sigma = model.eval_points_raw(points[i:i + chunk], coarse=coarse, precision=precision)
+        rgbs.append(rgb.cpu() if to_cpu else rgb)
+        sigmas.append(sigma.cpu() if to_cpu else sigma)
+    return torch.cat(rgbs, 0), torch.cat(sigmas, 0)
+
+
+def compute_psnr(mse):
+    """utils.compute_psnr (nerf_sh/nerf/utils.py:384-393)."""
+    return -10.0 * np.log(mse) / np.log(10.0)

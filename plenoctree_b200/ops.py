@@ -58,6 +58,19 @@ def eval_points(blob, sh_deg, points, viewdirs, precision=PREC_FP16):
     return out[:, :3], out[:, 3:4]
 
 
+def eval_cells_mean(blob, sh_deg, points, samples_per_cell, precision=PREC_FP16):
+    """extraction step 2 (octree/extraction.py:367-394): points [n_cells, S, 3] -> [n_cells, 3K+1] means."""
+    _f32c(points, "points")
+    pts = points.reshape(-1, 3)
+    if pts.shape[0] % samples_per_cell:
+        raise ValueError("points must hold samples_per_cell points per cell")
+    n_cells = pts.shape[0] // samples_per_cell
+    out = torch.empty((n_cells, 3 * K_of(sh_deg) + 1), dtype=torch.float32, device=points.device)
+    check(lib.pob_eval_cells_mean(ptr(blob), sh_deg, ptr(pts), n_cells, samples_per_cell, ptr(out), precision,
+                                  stream_ptr()))
+    return out
+
+
 def eval_grid(blob, sh_deg, reso, offset, scale, x0=0, nx=None, ny=None, nz=None, want_rgb=False,
               precision=PREC_FP16, device="cuda"):
     """Dense-grid sweep of octree.extraction (octree/extraction.py:244-320) for one x-slab."""

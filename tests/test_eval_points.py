@@ -166,3 +166,25 @@ def test_grid_sweep_matches_reference_grid_formula():
     _, sig_s = ops.eval_grid(blob, sh_deg, reso, offset.tolist(), scale.tolist(), x0=8, nx=12)
     torch.cuda.synchronize()
     assert torch.equal(sig_s, sig_p[8 * reso * reso:20 * reso * reso, 0])
+
+
+@pytest.mark.parametrize("S", [256, 32, 8, 5])
+def test_cell_mean_extraction_step2(S):
+    """octree/extraction.py:367-394: mean over samples_per_cell points of cat([raw_rgb, raw_sigma])."""
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200 import ops
+    sh_deg = 3
+    flat = O.init_flat_params(sh_deg, 41, bias_scale=0.05)
+    blob = _blob(flat, sh_deg)
+    n_cells = 97
+    rs = np.random.RandomState(S)
+    centers = rs.uniform(-1.4, 1.4, size=(n_cells, 1, 3)).astype(np.float32)
+    pts = (centers + rs.uniform(-0.003, 0.003, size=(n_cells, S, 3))).astype(np.float32)
+    with torch.no_grad():
+        rgb, sig = O.eval_points_raw(O.unflatten(flat, sh_deg), torch.from_numpy(pts.reshape(-1, 3)))
+        want = torch.cat([rgb, sig], -1).reshape(n_cells, S, -1).mean(1).numpy()
+    for prec, tol in ((ops.PREC_FP16X3, TOL_X3), (ops.PREC_FP16, TOL_FP16)):
+        got = ops.eval_cells_mean(blob, sh_deg, torch.from_numpy(pts).cuda(), S, precision=prec)
+        torch.cuda.synchronize()
+        assert got.shape == (n_cells, 49)
+        assert _relmax(got.cpu().numpy(), want) < tol

@@ -206,3 +206,52 @@ def test_nerf_forward_vs_oracle(sh_deg, nf):
                         assert e_rgb < 1e-3 and e_acc < 1e-3, (lvl, pname, randomized, pinned, e_rgb, e_acc)
                     else:
                         assert rel_rms < 1e-3 and psnr > 60 and e_rgb < 2e-2, (lvl, randomized, rel_rms, psnr, e_rgb)
+
+
+def test_full_frame_psnr_parity():
+    """north-star bar: PSNR of a rendered full frame within 0.05 dB of the reference path (oracle), measured
+    against the same target image (a teacher field rendered by the oracle).  64x64 frame, SH16, 64+128."""
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200 import ops
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf import utils as U
+    sh_deg, H, W = 3, 64, 64
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    pose = O.pose_spherical(40.0, -35.0, 4.0)[None]
+    rays = U.generate_rays(W, H, focal, pose)
+    o, d, v = (r[0].reshape(-1, 3) for r in rays)
+
+    def field(seed):
+        fc = O.init_flat_params(sh_deg, seed, bias_scale=0.05)
+        ff = O.init_flat_params(sh_deg, seed + 1, bias_scale=0.05)
+        off = O.param_count(sh_deg) - 48 - 1 - 256 * 48 - 256
+        for f in (fc, ff):
+            f[off:off + 256] *= 30.0
+        return fc, ff
+
+    def oracle_render(fc, ff):
+        outs = []
+        with torch.no_grad():
+            for i in range(0, H * W, 1024):
+                sl = tuple(torch.from_numpy(a[i:i + 1024]) for a in (o, d, v))
+                outs.append(O.nerf_forward(O.unflatten(fc, sh_deg), O.unflatten(ff, sh_deg), sh_deg, sl, 64, 128, 2.0,
+                                           6.0, True)[-1][0])
+        return torch.cat(outs).numpy()
+
+    target = oracle_render(*field(500))
+    fc, ff = field(600)
+    ref = oracle_render(fc, ff)
+    model = NerfModel(sh_deg=sh_deg, max_rays=2048)
+    model.set_params(np.concatenate([fc, ff]))
+    img = Rays(*[r[0] for r in rays])
+    psnr_ref = U.compute_psnr(float(((ref - target) ** 2).mean()))
+    for prec, pname in ((ops.PREC_FP16, "fp16"), (ops.PREC_FP16X3, "fp16x3")):
+        rgb, disp, acc = U.render_image(model, img, chunk=2048, precision=prec)
+        torch.cuda.synchronize()
+        got = rgb.reshape(-1, 3).cpu().numpy()
+        psnr_gpu = U.compute_psnr(float(((got - target) ** 2).mean()))
+        psnr_vs_ref = U.compute_psnr(float(((got - ref) ** 2).mean()))
+        _record(f"full_frame_{pname}", dict(psnr_gpu=float(psnr_gpu), psnr_ref=float(psnr_ref),
+                                             psnr_gpu_vs_ref=float(psnr_vs_ref)))
+        assert abs(psnr_gpu - psnr_ref) < 0.05, (pname, psnr_gpu, psnr_ref)
+        assert psnr_vs_ref > 55.0
