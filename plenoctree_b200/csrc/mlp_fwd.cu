@@ -60,8 +60,8 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return r;
 }
 
-__device__ __forceinline__ void load_point(const FwdParams& p, long long s, float& x, float& y,
-                                           float& z) {
+__device__ __noinline__ void load_point(const FwdParams& p, long long s, float& x, float& y,
+                                        float& z) {
   if (s >= p.M) s = p.M - 1;
   if (p.src_mode == SRC_POINTS) {
     const float* q = p.points + 3 * s;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void load_point(const FwdParams& p, long long s, floa
 // [x(3), sin(2^j x_c) j-major (30), sin(2^j x_c + pi/2) (30)], column 63 = 1 (bias carrier).
 // unit_lo/unit_hi: which 16-byte units (8 features each) this thread stores.
 template <int NSPLIT, bool PRECISE>
-__device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row, float x, float y,
+__device__ __noinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row, float x, float y,
                                            float z, int unit_lo, int unit_hi, uint8_t* e_glob = nullptr) {
   float f[64];
   f[0] = x;
@@ -137,30 +137,19 @@ __device__ __forceinline__ void posenc_row(uint8_t* e_hi, uint8_t* e_lo, int row
   }
 }
 
-// extraction step 2 (octree/extraction.py:367-394): accumulate value/S into out_cell[cell][idx].  When the
-// cell size is a multiple of the warp size all 32 rows of a warp belong to one cell: shuffle-reduce first.
-__device__ __forceinline__ void cell_accumulate(const FwdParams& p, long long s, int idx, float v) {
-  const float inv = 1.0f / float(p.cell_S);
-  const int width = 3 * p.K + 1;
-  if ((p.cell_S & 31) == 0) {
-    v = (s < p.M) ? v : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && s < p.M) atomicAdd(p.out_cell + (s / p.cell_S) * width + idx, v * inv);
-  } else if (s < p.M) {
-    atomicAdd(p.out_cell + (s / p.cell_S) * width + idx, v * inv);
-  }
-}
-
 __device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, uint32_t& n) {
   if (tr && blockIdx.x == 0 && n < 256) tr[role * 256 + n++] = clock64();
 }
 
 }  // namespace
 
-template <int NSPLIT, bool PRECISE>
+// OUTM (= p.out_mode) is a template parameter so that each instantiation carries only its own heads
+// epilogue: the fully unrolled 80-column heads loop with all four output modes inlined made the kernel
+// 145+ KB of SASS and cost ~8 % of inference throughput in instruction-cache misses.
+template <int NSPLIT, int OUTM, bool SAVE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  constexpr bool PRECISE = (NSPLIT == 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) Barriers bars;
   __shared__ uint32_t tmem_base_s;
@@ -307,7 +296,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     uint8_t* const e_lo = smem + SM_E1;
     const int unit_lo = (NSPLIT == 1) ? 0 : 4 * g, unit_hi = (NSPLIT == 1) ? 8 : 4 * g + 4;
     const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(tile_in_iter) * 256u;
-    const bool saving = (NSPLIT == 1) && (p.save_h != nullptr);
+    constexpr bool saving = SAVE;   // training launches (NSPLIT == 1): store h_l tiles, posenc tiles and relu masks
     uint32_t dphase = 0, tn = 0;
     const bool tracer = (warp & 3) == 0 && lane == 0;
     unsigned long long* const trp = tracer ? p.trace : nullptr;
@@ -430,15 +419,16 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         float basis[25];
         float* stage = nullptr;
         int P = 0;
-        if (p.out_mode == OUT_RGBS) {
+
+        if (OUTM == OUT_RGBS) {
           long long sc = s < p.M ? s : p.M - 1;
           long long vi = (p.src_mode == SRC_RAYS) ? sc / p.n_per_ray : sc;
           const float* vd = p.viewdirs + 3 * vi;
           if (p.sh_deg >= 0) sh_basis(p.sh_deg, __ldg(vd), __ldg(vd + 1), __ldg(vd + 2), basis);
           else basis[0] = 1.f;
-        } else if (p.out_mode == OUT_RAW) {
+        } else if (OUTM == OUT_RAW || OUTM == OUT_CELL_MEAN) {
           // per-warp staging area inside this group's (now dead) activation tile
-          P = (3 * K) | 1;  // odd pitch (3K or 3K+1) -> conflict-free scalar stores
+          P = (3 * K + 1) | 1;  // odd pitch -> conflict-free scalar stores
           stage = reinterpret_cast<float*>(a_hi + (warp & 3) * 16384) + lane * P;
         }
 #pragma unroll
@@ -456,15 +446,15 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
                 const int k = (n - 1) / 3, c = (n - 1) % 3;
                 if (k < K) {
                   const float coef = __uint_as_float(v[jj]);
-                  if (p.out_mode == OUT_RGBS) pre[c] = fmaf(basis[k < 25 ? k : 24], coef, pre[c]);
-                  else if (p.out_mode == OUT_RAW) stage[c * K + k] = coef;
-                  else if (p.out_mode == OUT_CELL_MEAN) cell_accumulate(p, s, c * K + k, coef);
+                  if (OUTM == OUT_RGBS) pre[c] = fmaf(basis[k < 25 ? k : 24], coef, pre[c]);
+                  else if (OUTM == OUT_RAW) stage[c * K + k] = coef;
+                  else if (OUTM == OUT_CELL_MEAN) stage[c * K + k] = coef;
                 }
               }
             }
           }
         }
-        if (p.out_mode == OUT_RGBS) {
+        if (OUTM == OUT_RGBS) {
           if (s < p.M) {
             float4 o;
             o.x = 1.f / (1.f + expf(-pre[0]));
@@ -473,11 +463,36 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             o.w = fmaxf(sigma_raw, 0.f);
             p.out_rgbs[s] = o;
           }
-        } else if (p.out_mode == OUT_CELL_MEAN) {
-          cell_accumulate(p, s, 3 * K, sigma_raw);
+        } else if (OUTM == OUT_CELL_MEAN) {
+          // extraction step 2 (octree/extraction.py:367-394): out[cell] += cat([raw_rgb, raw_sigma]) / S.
+          // The warp's 32 rows sit in the staging area; lanes own output columns and sum over rows (one
+          // cell per warp when S is a multiple of 32), then one atomicAdd per column.
+          stage[3 * K] = sigma_raw;
+          __syncwarp();
+          const float* wstage = reinterpret_cast<const float*>(a_hi + (warp & 3) * 16384);
+          const long long row0 = tile_idx * TILE_M + (warp & 3) * 32;
+          const int width = 3 * K + 1;
+          const float inv = 1.0f / float(p.cell_S);
+          if ((p.cell_S & 31) == 0) {
+            if (row0 < p.M) {
+              float* dst = p.out_cell + (row0 / p.cell_S) * width;
+              for (int i = lane; i < width; i += 32) {
+                float acc = 0.f;
+                for (int rr = 0; rr < 32; ++rr) acc += wstage[rr * P + i];
+                atomicAdd(dst + i, acc * inv);
+              }
+            }
+          } else {
+            for (int rr = 0; rr < 32; ++rr) {
+              if (row0 + rr >= p.M) break;
+              float* dst = p.out_cell + ((row0 + rr) / p.cell_S) * width;
+              for (int i = lane; i < width; i += 32) atomicAdd(dst + i, wstage[rr * P + i] * inv);
+            }
+          }
+          __syncwarp();
         } else {
           if (s < p.M) p.out_sigma[s] = sigma_raw;
-          if (p.out_mode == OUT_RAW) {
+          if (OUTM == OUT_RAW) {
             __syncwarp();
             const float* wstage = reinterpret_cast<const float*>(a_hi + (warp & 3) * 16384);
             const long long row0 = tile_idx * TILE_M + (warp & 3) * 32;
@@ -507,6 +522,7 @@ cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int
   const int rows = (nsplit == 1) ? 2 * TILE_M : TILE_M;
   long long iters = (p.M + rows - 1) / rows;
   int grid = int(iters < num_sms ? iters : num_sms);
+  (void)precise_sin;   // tied to the precision mode: FP16X3 uses libdevice sinf, FP16 the reduced SFU sine
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e =
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
@@ -514,12 +530,26 @@ cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int
     kernel<<<grid, FWD_THREADS, SM_TOTAL, stream>>>(p);
     return cudaGetLastError();
   };
-  if (nsplit == 1) {
-    return precise_sin ? launch(mlp_fwd_kernel<1, true>) : launch(mlp_fwd_kernel<1, false>);
-  } else if (nsplit == 3) {
-    return precise_sin ? launch(mlp_fwd_kernel<3, true>) : launch(mlp_fwd_kernel<3, false>);
+  if (nsplit != 1 && nsplit != 3) return cudaErrorInvalidValue;
+  const bool save = p.save_h != nullptr;
+  if (save && (nsplit != 1 || !p.save_e || !p.save_mask ||
+               (p.out_mode != OUT_RGBS && p.out_mode != OUT_SIGMA)))
+    return cudaErrorInvalidValue;
+  switch (p.out_mode) {
+    case OUT_RAW:
+      return nsplit == 1 ? launch(mlp_fwd_kernel<1, OUT_RAW, false>) : launch(mlp_fwd_kernel<3, OUT_RAW, false>);
+    case OUT_SIGMA:
+      if (save) return launch(mlp_fwd_kernel<1, OUT_SIGMA, true>);
+      return nsplit == 1 ? launch(mlp_fwd_kernel<1, OUT_SIGMA, false>) : launch(mlp_fwd_kernel<3, OUT_SIGMA, false>);
+    case OUT_RGBS:
+      if (save) return launch(mlp_fwd_kernel<1, OUT_RGBS, true>);
+      return nsplit == 1 ? launch(mlp_fwd_kernel<1, OUT_RGBS, false>) : launch(mlp_fwd_kernel<3, OUT_RGBS, false>);
+    case OUT_CELL_MEAN:
+      return nsplit == 1 ? launch(mlp_fwd_kernel<1, OUT_CELL_MEAN, false>)
+                         : launch(mlp_fwd_kernel<3, OUT_CELL_MEAN, false>);
+    default:
+      return cudaErrorInvalidValue;
   }
-  return cudaErrorInvalidValue;
 }
 
 }  // namespace pob
