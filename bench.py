@@ -300,6 +300,8 @@ def main():
     dom = max(alg, key=lambda k: per_step_ms[k])
     peaks = measured_peaks()
     achieved = alg[dom] / (per_step_ms[dom] * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel class, per step, from the committed
+    # `ncu --set full` capture (profiles/r1_dram_traffic.json; scaled there to the 4096-ray step)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
     if os.path.exists(tpath):
