@@ -109,6 +109,22 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 // ----------------------------------------------------------------------------------
+// Inter-CTA flags in global memory (producer/consumer queues of the fused backward kernel)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes (by any SM, made visible by an acquire) -> async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------
 // Bulk async copies (TMA, 1-D).  SASS: UBLKCP.
 // ----------------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,

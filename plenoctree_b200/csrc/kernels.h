@@ -89,6 +89,20 @@ cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const floa
 cudaError_t launch_sparsity_grad(const float* sigma_raw, int n, float length, float coef, float4* G,
                                  float* exp_sum, cudaStream_t st);
 
+// ---- producer/consumer queues of the fused dgrad+wgrad kernel (mlp_bwdw.cu) -------------------
+// Producer CTA p hands every dZ_l / dO tile pair of its current iteration to the layer-owning consumer
+// CTAs through a per-(producer, layer) double slot in global memory that is rewritten every iteration
+// (so it stays L2 resident) instead of a [ntile][8] array in HBM.
+constexpr int BWDW_QUEUES = 9;          // 0 = dO, 1 + (7 - l) = dZ_l  (order of production)
+struct BwdwQueues {
+  uint8_t* slots;           // [NP][9][2 tiles][64 KB]      (null = classic two-kernel path)
+  uint32_t* produced;       // [NP][9][2]   iterations written   (release/acquire, gpu scope)
+  uint32_t* consumed;       // [NP][9][2]   iterations consumed per reader (dZ_5 has two readers)
+  int NP;                   // number of producer CTAs = first consumer CTA
+};
+inline size_t bwdw_slot_bytes(int NP) { return size_t(NP) * BWDW_QUEUES * 2 * 65536; }
+inline size_t bwdw_flag_count(int NP) { return size_t(NP) * BWDW_QUEUES * 2; }
+
 // ---- mlp_bwd.cu -----------------------------------------------------------------------------
 struct BwdParams {
   long long M;
@@ -100,6 +114,7 @@ struct BwdParams {
   const uint32_t* mask;     // [8][Mpad][8] from mlp_fwd
   uint8_t* save_dz;         // [ntile][8][64 KB]
   uint8_t* save_do;         // [ntile][32 KB]
+  BwdwQueues q;             // fused path: tiles go to the queues instead of save_dz / save_do
 };
 cudaError_t launch_mlp_bwd(const BwdParams& p, int num_sms, cudaStream_t stream);
 
@@ -116,17 +131,23 @@ struct WgradParams {
   int NH;
   float* partials;          // [num_ctas][WG_PARTIAL_FLOATS]
   short cta_role[WG_MAX_CTAS], cta_index[WG_MAX_CTAS], cta_count[WG_MAX_CTAS];
+  BwdwQueues q;             // fused path: A (or, for the heads, B) operand tiles come from the queues
+  long long num_iters;      // fused path: producer iterations (tile pairs) of the launch
 };
 // role -> [first CTA, count]; fills the per-CTA tables of `p`; returns number of CTAs to launch
 int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES],
                        int role_count[WG_NUM_ROLES]);
 cudaError_t launch_mlp_wgrad(const WgradParams& p, int num_ctas, cudaStream_t stream);
+// fused dgrad + wgrad: CTAs [0, q.NP) run the dgrad chain, CTAs [q.NP, q.NP + num_consumers) the wgrad roles
+// (cta_role/index/count are indexed by consumer number = blockIdx.x - q.NP)
+cudaError_t launch_mlp_bwdw(const BwdParams& b, const WgradParams& w, int num_consumers, cudaStream_t stream);
+int wgrad_assign_roles_n(WgradParams& p, int n, int role_start[WG_NUM_ROLES], int role_count[WG_NUM_ROLES]);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 // partials of one wgrad launch -> flat gradient of one MLP (reference layout), times inv_scale
 cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_NUM_ROLES],
                                 const int role_count[WG_NUM_ROLES], int K, float inv_scale,
-                                float* grad_flat, cudaStream_t stream);
+                                float* grad_flat, cudaStream_t stream, const float* partials2 = nullptr);
 // flax.optim.Adam.apply_gradient on a flat buffer; grad is multiplied by grad_mult first
 cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, long long n, float lr,
                         float step, float beta1, float beta2, float eps, float grad_mult,

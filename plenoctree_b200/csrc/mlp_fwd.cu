@@ -379,21 +379,23 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
             mp[1] = make_uint4(maskw[NCH - 4], maskw[NCH - 3], maskw[NCH - 2], maskw[NCH - 1]);
           }
-          // h_l tile -> global: the shared-memory image already has the final layout, so the group's 128
-          // threads copy it linearly (coalesced 512 B per warp instruction) BEFORE the tile is handed to
-          // the MMA warp; a bulk store issued here instead would read shared memory during the next
-          // layer's MMAs and halve their rate (profiles/r1: MMA phase 4.4k -> 9.4k cycles).
-          named_bar_sync(1 + g, 128);
-          {
-            const int t = int(threadIdx.x & 127);
-            const uint4* src = reinterpret_cast<const uint4*>(a_hi) + t;
-            uint4* dst = reinterpret_cast<uint4*>(h_glob) + t;
-#pragma unroll 8
-            for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
-          }
         }
         signal_a_ready();
         trace_stamp(trp, trole, tn);             // a_ready signalled
+        if (saving) {
+          // h_l tile -> global.  The shared-memory image already has the final layout, so the group's 128
+          // threads copy it linearly (coalesced 512 B per warp instruction).  The copy runs AFTER the tile has
+          // been handed to the MMA warp, in the shadow of the next layer's MMAs: an SM can push only ~32 B/clk
+          // to L2, so 2 x 64 KB take ~4.1k cycles per layer; LSU-paced reads of the tile disturb the MMA's
+          // operand fetches far less than a bulk (TMA) store of it did (MMA phase 4.4k -> 9.4k cycles).
+          named_bar_sync(1 + g, 128);
+          const int t = int(threadIdx.x & 127);
+          const uint4* src = reinterpret_cast<const uint4*>(a_hi) + t;
+          uint4* dst = reinterpret_cast<uint4*>(h_glob) + t;
+#pragma unroll 8
+          for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
+          named_bar_sync(1 + g, 128);   // all copies done before any warp's next epilogue overwrites the tile
+        }
         if (l == SKIP_LAYER) {
           // E is dead until the next iteration: encode the next tile now, in the shadow of the
           // layer-6/7/heads MMAs.

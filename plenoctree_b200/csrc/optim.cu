@@ -10,7 +10,12 @@ namespace pob {
 // (128 KB per tile for the 256x256 layers, ~80-96 KB for Dense_0 / the skip rows / the heads).
 int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES],
                        int role_count[WG_NUM_ROLES]) {
-  int n = num_sms < WG_MAX_CTAS ? num_sms : WG_MAX_CTAS;
+  return wgrad_assign_roles_n(p, num_sms, role_start, role_count);
+}
+
+int wgrad_assign_roles_n(WgradParams& p, int n_in, int role_start[WG_NUM_ROLES],
+                         int role_count[WG_NUM_ROLES]) {
+  int n = n_in < WG_MAX_CTAS ? n_in : WG_MAX_CTAS;
   if (n < WG_NUM_ROLES) n = WG_NUM_ROLES;  // one CTA per role at the very least (they time-share SMs)
   int small = (n * 8) / 100;               // per small role
   if (small < 1) small = 1;
@@ -29,6 +34,11 @@ int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES]
       p.cta_count[cta] = short(c);
     }
   }
+  for (int i = cta; i < WG_MAX_CTAS; ++i) {   // spare CTAs idle (role -1)
+    p.cta_role[i] = -1;
+    p.cta_index[i] = 0;
+    p.cta_count[i] = 1;
+  }
   return cta;
 }
 
@@ -36,6 +46,7 @@ namespace {
 
 struct ReduceArgs {
   const float* partials;
+  const float* partials2;   // optional second launch with the same role tables (sparsity level)
   int role_start[WG_NUM_ROLES], role_count[WG_NUM_ROLES];
   FlatLayout L;
   int K, NH;
@@ -95,6 +106,10 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a) {
   float s = 0.f;
   const float* p = a.partials + size_t(a.role_start[role]) * WG_PARTIAL_FLOATS + off;
   for (int c = 0; c < a.role_count[role]; ++c) s += p[size_t(c) * WG_PARTIAL_FLOATS];
+  if (a.partials2) {
+    const float* p2 = a.partials2 + size_t(a.role_start[role]) * WG_PARTIAL_FLOATS + off;
+    for (int c = 0; c < a.role_count[role]; ++c) s += p2[size_t(c) * WG_PARTIAL_FLOATS];
+  }
   a.grad[e] = s * a.inv_scale;
 }
 
@@ -117,9 +132,10 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 
 cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_NUM_ROLES],
                                 const int role_count[WG_NUM_ROLES], int K, float inv_scale,
-                                float* grad_flat, cudaStream_t stream) {
+                                float* grad_flat, cudaStream_t stream, const float* partials2) {
   ReduceArgs a;
   a.partials = partials;
+  a.partials2 = partials2;
   for (int r = 0; r < WG_NUM_ROLES; ++r) {
     a.role_start[r] = role_start[r];
     a.role_count[r] = role_count[r];

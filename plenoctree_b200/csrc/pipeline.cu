@@ -34,10 +34,37 @@ struct Level {
 
 struct Workspace {
   Level lv[3];        // coarse, fine, sparsity
-  float* partials[2];
-  float* u_or_tmp;
+  float* partials[3]; // wgrad partials of the coarse / fine / sparsity launches
+  uint8_t* q_slots;   // fused backward: producer->consumer tile queues (L2 resident)
+  uint32_t* q_flags;  // produced[NP*9*2] then consumed[NP*9*2]
   size_t total;
 };
+
+#include <cstdlib>
+// Fused backward (dgrad producers + wgrad consumers in one launch, dZ tiles through L2-resident queues).
+// Correct (same parity tests) but, as of round 1, slower than the two-kernel path (3.1 vs 2.7 ms per step:
+// with ~80 of 148 SMs producing, the serialized MMA / epilogue / copy-out phases of a producer bound the
+// launch), so it is opt-in: POB_FUSED_BWD=1, producer count POB_BWDW_NP.
+bool fused_bwd_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POB_FUSED_BWD");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+int fused_bwd_producers(int sms) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POB_BWDW_NP");
+    v = e ? atoi(e) : 0;
+  }
+  int np = v > 0 ? v : (sms * 59 + 50) / 100;   // dgrad : wgrad work ~ 0.59 : 0.41 (measured cycle counts)
+  if (np > sms - WG_NUM_ROLES) np = sms - WG_NUM_ROLES;
+  if (np < 1) np = 1;
+  return np;
+}
+constexpr int MAX_PRODUCERS = 160;
 
 size_t up(size_t x) { return (x + 1023) / 1024 * 1024; }
 
@@ -81,7 +108,9 @@ Workspace carve(const pob_render_config& c, int training, uint8_t* base) {
     }
   }
   if (training) {
-    for (int i = 0; i < 2; ++i) w.partials[i] = (float*)take(sizeof(float) * WG_MAX_CTAS * WG_PARTIAL_FLOATS);
+    for (int i = 0; i < 3; ++i) w.partials[i] = (float*)take(sizeof(float) * WG_MAX_CTAS * WG_PARTIAL_FLOATS);
+    w.q_slots = take(bwdw_slot_bytes(MAX_PRODUCERS));
+    w.q_flags = (uint32_t*)take(2 * bwdw_flag_count(MAX_PRODUCERS) * sizeof(uint32_t));
   }
   w.total = off;
   return w;
@@ -258,8 +287,9 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     const float coef = hp->loss_scale * hp->sparsity_weight * hp->sparsity_length / float(sp_n);
     { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sparsity_grad(S.sigma, int(sp_n), hp->sparsity_length, coef, S.G, stats_dev + 2, st)); }
   }
-  // ---- dgrad chains ----
-  auto bwd = [&](const void* pk, Level& L, long long M, const float* vd, int npr) -> cudaError_t {
+  // ---- backward ----
+  const int NH = heads_width(K);
+  auto make_bwd = [&](const void* pk, Level& L, long long M, const float* vd, int npr) {
     BwdParams b;
     memset(&b, 0, sizeof(b));
     b.M = M;
@@ -274,15 +304,72 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     b.mask = L.mask;
     b.save_dz = L.DZ;
     b.save_do = L.DO;
+    return b;
+  };
+  struct Job {
+    const void* pk;
+    Level* L;
+    long long M;
+    const float* vd;
+    int npr;
+    int mlp;
+  };
+  Job jobs[3];
+  int njobs = 0;
+  jobs[njobs++] = Job{packed_coarse_dev, &C, (long long)n_rays * Nc, viewdirs_dev, Nc, 0};
+  if (Nf > 0) jobs[njobs++] = Job{packed_fine_dev, &F, (long long)n_rays * (Nc + Nf), viewdirs_dev, Nc + Nf, 1};
+  if (sparsity) jobs[njobs++] = Job{pk_main, &S, sp_n, sp_points_dev, 0, Nf > 0 ? 1 : 0};
+
+  if (fused_bwd_enabled() && sms >= 2 * WG_NUM_ROLES) {
+    // One persistent launch per level: dgrad producers + layer-owning wgrad consumers, dZ tiles through
+    // L2-resident queues.  Partials of the launches that feed the same MLP are summed by reduce_grads.
+    const int NP = fused_bwd_producers(sms);
+    const int NC = sms - NP;
+    int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];
+    const float* part_of_mlp[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    for (int j = 0; j < njobs; ++j) {
+      Job& J = jobs[j];
+      BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
+      b.q.slots = w.q_slots;
+      b.q.produced = w.q_flags;
+      b.q.consumed = w.q_flags + bwdw_flag_count(MAX_PRODUCERS);
+      b.q.NP = NP;
+      WgradParams g;
+      memset(&g, 0, sizeof(g));
+      g.seg[0] = WgradSegment{J.L->H, J.L->DZ, J.L->E, J.L->DO};
+      g.seg_tiles[0] = tiles_for(J.M);
+      g.NH = NH;
+      g.partials = w.partials[j];
+      g.q = b.q;
+      g.num_iters = (J.M + 2 * TILE_M - 1) / (2 * TILE_M);
+      wgrad_assign_roles_n(g, NC, rs, rc);
+      POB_CUDA(where, cudaMemsetAsync(w.q_flags, 0, 2 * bwdw_flag_count(MAX_PRODUCERS) * sizeof(uint32_t), st));
+      {
+        pob_count_launch();
+        PobPhaseTimer _t(POB_PH_BWD, st);
+        POB_CUDA(where, launch_mlp_bwdw(b, g, NC, st));
+      }
+      const float** slot = part_of_mlp[J.mlp];
+      if (!slot[0]) slot[0] = w.partials[j];
+      else slot[1] = w.partials[j];
+    }
+    for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
+      pob_count_launch();
+      PobPhaseTimer _t(POB_PH_OPTIM, st);
+      POB_CUDA(where, launch_reduce_grads(part_of_mlp[mlp][0], rs, rc, K, 1.0f / hp->loss_scale,
+                                          grad_flat_dev + size_t(mlp) * P, st, part_of_mlp[mlp][1]));
+    }
+    return 0;
+  }
+
+  // ---- classic path: dgrad launches, then one wgrad launch per MLP over the saved dZ / h tiles ----
+  for (int j = 0; j < njobs; ++j) {
+    Job& J = jobs[j];
+    BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
     pob_count_launch();
     PobPhaseTimer _t(POB_PH_BWD, st);
-    return launch_mlp_bwd(b, sms, st);
-  };
-  POB_CUDA(where, bwd(packed_coarse_dev, C, (long long)n_rays * Nc, viewdirs_dev, Nc));
-  if (Nf > 0) POB_CUDA(where, bwd(packed_fine_dev, F, (long long)n_rays * (Nc + Nf), viewdirs_dev, Nc + Nf));
-  if (sparsity) POB_CUDA(where, bwd(pk_main, S, sp_n, sp_points_dev, 0));
-  // ---- wgrad + reduce, one launch per MLP ----
-  const int NH = heads_width(K);
+    POB_CUDA(where, launch_mlp_bwd(b, sms, st));
+  }
   for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
     WgradParams g;
     memset(&g, 0, sizeof(g));
@@ -299,8 +386,8 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     g.partials = w.partials[mlp];
     int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];
     const int nctas = wgrad_assign_roles(g, sms, rs, rc);
-    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_WGRAD, st); POB_CUDA(where, launch_mlp_wgrad(g, nctas, st)); }
-    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
+    { pob_count_launch(); PobPhaseTimer _t(POB_PH_WGRAD, st); POB_CUDA(where, launch_mlp_wgrad(g, nctas, st)); }
+    { pob_count_launch(); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
                                         grad_flat_dev + size_t(mlp) * P, st)); }
   }
   return 0;
