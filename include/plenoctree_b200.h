@@ -164,6 +164,11 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
                       const float* sp_points_dev, float* grad_flat_dev, float* stats_dev, void* workspace_dev,
                       void* stream);
 
+/* Profiling aid for the opt-in fused backward (POB_FUSED_BWD=1): copies the per-CTA cycle counters of the last
+ * pob_loss_and_grad call to out_host[3 launches][256 CTAs][4]  (producers: {spin tile X, spin tile Y, total X,
+ * total Y}; consumers: {waiting for producers, waiting for a free stage, total, role}). */
+int pob_debug_bwdw_stalls(const pob_render_config* cfg, void* workspace_dev, unsigned long long* out_host);
+
 /* flax.optim.Adam (beta1 .9, beta2 .999, eps 1e-8; nerf_sh/nerf/models.py:44) on the flat buffers of
  * num_mlps MLPs, g = grad*grad_mult + weight_decay_coef*param, then re-packs the operand blobs.
  * `step` = number of updates already applied (flax optimizer.state.step). */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pob_render_rays": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _i, _vp]),
     "pob_loss_and_grad": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _fp,
                                _vp, _vp]),
+    "pob_debug_bwdw_stalls": (_i, [_vp, _vp, _vp]),
     "pob_adam_update": (_i, [_i, _i, _fp, _fp, _fp, _fp, _c.c_float, _c.c_float, _c.c_float, _c.c_float,
                              _vp, _vp, _vp]),
     "pob_umma_probe": (_i, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i, _u32, _i, _fp, _vp]),

@@ -134,14 +134,18 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem, cons
     auto q_slot = [&](int qi) -> uint8_t* {
       return p.q.slots + ((size_t(cta) * BWDW_QUEUES + qi) * 2 + g) * A_TILE_BYTES;
     };
+    long long stall_cycles = 0;
+    const long long t_begin = clock64();
     auto q_wait_free = [&](int qi) {
       if (fused && flagger) {
+        const long long t0 = clock64();
         const uint32_t* c = p.q.consumed + (size_t(cta) * BWDW_QUEUES + qi) * 2;
         while (ld_acquire_gpu(c) < kiter) {
         }
         if (qi == 1 + (7 - SKIP_LAYER))   // dZ_5 has a second reader (the skip rows of Dense_5)
           while (ld_acquire_gpu(c + 1) < kiter) {
           }
+        stall_cycles += clock64() - t0;
       }
     };
     // after a tile copy: every thread of the group is done reading a_tile (the next epilogue may overwrite
@@ -267,6 +271,10 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem, cons
         }
         q_publish(1 + (7 - l));
       }
+    }
+    if (fused && p.q.stall && (threadIdx.x & 127) == 0) {
+      p.q.stall[size_t(cta) * 4 + g] = (unsigned long long)stall_cycles;
+      p.q.stall[size_t(cta) * 4 + 2 + g] = (unsigned long long)(clock64() - t_begin);
     }
   }
 

@@ -99,6 +99,7 @@ struct BwdwQueues {
   uint32_t* produced;       // [NP][9][2]   iterations written   (release/acquire, gpu scope)
   uint32_t* consumed;       // [NP][9][2]   iterations consumed per reader (dZ_5 has two readers)
   int NP;                   // number of producer CTAs = first consumer CTA
+  unsigned long long* stall; // optional [grid][4] cycle counters: spin time on flags / total (profiling)
 };
 inline size_t bwdw_slot_bytes(int NP) { return size_t(NP) * BWDW_QUEUES * 2 * 65536; }
 inline size_t bwdw_flag_count(int NP) { return size_t(NP) * BWDW_QUEUES * 2; }

@@ -37,6 +37,7 @@ struct Workspace {
   float* partials[3]; // wgrad partials of the coarse / fine / sparsity launches
   uint8_t* q_slots;   // fused backward: producer->consumer tile queues (L2 resident)
   uint32_t* q_flags;  // produced[NP*9*2] then consumed[NP*9*2]
+  unsigned long long* q_stall;   // [3 jobs][160+][4] profiling counters of the fused backward
   size_t total;
 };
 
@@ -111,6 +112,7 @@ Workspace carve(const pob_render_config& c, int training, uint8_t* base) {
     for (int i = 0; i < 3; ++i) w.partials[i] = (float*)take(sizeof(float) * WG_MAX_CTAS * WG_PARTIAL_FLOATS);
     w.q_slots = take(bwdw_slot_bytes(MAX_PRODUCERS));
     w.q_flags = (uint32_t*)take(2 * bwdw_flag_count(MAX_PRODUCERS) * sizeof(uint32_t));
+    w.q_stall = (unsigned long long*)take(3 * 256 * 4 * sizeof(unsigned long long));
   }
   w.total = off;
   return w;
@@ -334,6 +336,7 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
       b.q.produced = w.q_flags;
       b.q.consumed = w.q_flags + bwdw_flag_count(MAX_PRODUCERS);
       b.q.NP = NP;
+      b.q.stall = w.q_stall + size_t(j) * 256 * 4;
       WgradParams g;
       memset(&g, 0, sizeof(g));
       g.seg[0] = WgradSegment{J.L->H, J.L->DZ, J.L->E, J.L->DO};
@@ -390,6 +393,15 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     { pob_count_launch(); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
                                         grad_flat_dev + size_t(mlp) * P, st)); }
   }
+  return 0;
+}
+
+int pob_debug_bwdw_stalls(const pob_render_config* cfg, void* workspace_dev, unsigned long long* out_host) {
+  if (check_cfg("pob_debug_bwdw_stalls", cfg)) return 1;
+  if (!workspace_dev || !out_host) return pob_fail("pob_debug_bwdw_stalls", "NULL pointer");
+  Workspace w = carve(*cfg, 1, (uint8_t*)workspace_dev);
+  POB_CUDA("pob_debug_bwdw_stalls", cudaMemcpy(out_host, w.q_stall, 3 * 256 * 4 * sizeof(unsigned long long),
+                                               cudaMemcpyDeviceToHost));
   return 0;
 }
 

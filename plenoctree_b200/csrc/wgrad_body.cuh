@@ -170,16 +170,22 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
     // ================================ loader ====================================
     // whole-warp control flow, one elected lane issues (see mlp_fwd.cu)
     uint32_t st = 0, phase = 0;
+    long long stall_cycles = 0, ring_cycles = 0;
+    const long long t_begin = clock64();
     for (long long i = 0; i < n_items; ++i) {
       const WgItem it = get_item(i);
       if (!it.valid) continue;
       if (it.wait_flag) {
+        const long long t0 = clock64();
         while (ld_acquire_gpu(it.wait_flag) < it.wait_val) {
         }
+        stall_cycles += clock64() - t0;
         fence_proxy_async_all();   // the producer's st.global data -> our bulk-copy (async proxy) reads
       }
       for (int sub = 0; sub < 2; ++sub) {
+        const long long t1 = clock64();
         mbar_wait(smem_u32(&bars.empty[st]), phase ^ 1);
+        ring_cycles += clock64() - t1;
         if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&bars.full[st]), WG_HALF + b_half_bytes);
           const uint32_t dst = sbase + st * WG_STAGE_BYTES;
@@ -198,6 +204,13 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
           phase ^= 1;
         }
       }
+    }
+    if (fused && p.q.stall && lane == 0) {
+      unsigned long long* s = p.q.stall + size_t(p.q.NP + cta) * 4;
+      s[0] = (unsigned long long)stall_cycles;     // waiting for producers
+      s[1] = (unsigned long long)ring_cycles;      // waiting for a free smem stage (MMA / bias warps behind)
+      s[2] = (unsigned long long)(clock64() - t_begin);
+      s[3] = (unsigned long long)role;
     }
   } else if (warp == 5) {
     // ================================= MMA ======================================
