@@ -194,6 +194,14 @@ int pob_umma_probe(const void* a_img_dev, uint32_t a_bytes, const void* b_img_de
                    const uint64_t* bdesc_dev, const uint32_t* dcol_dev, const uint32_t* accum_dev,
                    int nops, uint32_t idesc, int out_cols, float* out_dev, void* stream);
 
+/* CTA-pair variant (tcgen05 cta_group::2, cluster of two CTAs, M = 256 in idesc): CTA r stages
+ * a_img + r*a_bytes and b_img + r*b_bytes (its 128 A rows and its half of the B rows) at the same
+ * shared-memory offsets; returns the [256 x out_cols] accumulator (rows 128r.. from CTA r). */
+int pob_umma_probe_pair(const void* a_img_dev, uint32_t a_bytes, const void* b_img_dev,
+                        uint32_t b_bytes, uint32_t b_off, const uint64_t* adesc_dev,
+                        const uint64_t* bdesc_dev, const uint32_t* dcol_dev, const uint32_t* accum_dev,
+                        int nops, uint32_t idesc, int out_cols, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,4 +403,20 @@ int pob_umma_probe(const void* a_img_dev, uint32_t a_bytes, const void* b_img_de
   return 0;
 }
 
+int pob_umma_probe_pair(const void* a_img_dev, uint32_t a_bytes, const void* b_img_dev,
+                        uint32_t b_bytes, uint32_t b_off, const uint64_t* adesc_dev,
+                        const uint64_t* bdesc_dev, const uint32_t* dcol_dev, const uint32_t* accum_dev,
+                        int nops, uint32_t idesc, int out_cols, float* out_dev, void* stream) {
+  if (sm_count() <= 0) return fail("pob_umma_probe_pair", "no sm_100 CUDA device");
+  if (a_bytes % 16 || b_bytes % 16 || b_off % 1024 || b_off < a_bytes ||
+      (size_t)b_off + b_bytes > 200 * 1024)
+    return fail("pob_umma_probe_pair", "bad image sizes/offsets");
+  if (out_cols <= 0 || out_cols > 512) return fail("pob_umma_probe_pair", "out_cols out of range");
+  POB_CUDA("pob_umma_probe_pair",
+           pob::launch_umma_probe_pair(a_img_dev, a_bytes, b_img_dev, b_bytes, b_off, adesc_dev,
+                                       bdesc_dev, dcol_dev, accum_dev, nops, idesc, out_cols, out_dev,
+                                       (cudaStream_t)stream));
+  return 0;
+}
+
 }  // extern "C"

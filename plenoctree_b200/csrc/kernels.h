@@ -73,6 +73,11 @@ cudaError_t launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b
                               const uint64_t* bdesc, const uint32_t* dcol, const uint32_t* accum,
                               int nops, uint32_t idesc, int out_cols, float* out,
                               cudaStream_t stream);
+cudaError_t launch_umma_probe_pair(const void* a_img, uint32_t a_bytes, const void* b_img,
+                              uint32_t b_bytes, uint32_t b_off, const uint64_t* adesc,
+                              const uint64_t* bdesc, const uint32_t* dcol, const uint32_t* accum,
+                              int nops, uint32_t idesc, int out_cols, float* out,
+                              cudaStream_t stream);
 
 
 // ---- render.cu ------------------------------------------------------------------------------

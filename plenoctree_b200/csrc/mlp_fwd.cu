@@ -326,8 +326,10 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         dphase ^= 1;
         tc_fence_after();
         trace_stamp(trp, trole, tn);             // d_ready observed
-        // training: h_l tiles go to global memory straight from the registers (a bulk store out of
-        // shared memory competes with the next layer's MMA operand reads and halves the MMA rate)
+        // training: h_l tiles go to global memory straight from the epilogue registers, in the "T" layout
+        // (layouts.py: t_tile_offset) that mlp_wgrad reads MN-major without swizzle.  Copying the tile out of
+        // shared memory instead (bulk store, or LDS + STG) competes with the next layer's MMA operand reads:
+        // the SS-mode MMA alone needs 96 of the 128 B/clk of shared-memory bandwidth.
         uint8_t* const h_glob = saving ? p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES : nullptr;
         uint32_t maskw[8];
         constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
@@ -357,6 +359,9 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
                                  ((unit ^ uint32_t(row & 7)) << 4);
             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (saving)   // T layout: [32-row group][8-column unit][row][16 B] -> 512 contiguous bytes per warp store
+              *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
+                  make_uint4(w[0], w[1], w[2], w[3]);
             if (NSPLIT == 3) {
               uint32_t wl[4];
 #pragma unroll
@@ -382,20 +387,6 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         }
         signal_a_ready();
         trace_stamp(trp, trole, tn);             // a_ready signalled
-        if (saving) {
-          // h_l tile -> global.  The shared-memory image already has the final layout, so the group's 128
-          // threads copy it linearly (coalesced 512 B per warp instruction).  The copy runs AFTER the tile has
-          // been handed to the MMA warp, in the shadow of the next layer's MMAs: an SM can push only ~32 B/clk
-          // to L2, so 2 x 64 KB take ~4.1k cycles per layer; LSU-paced reads of the tile disturb the MMA's
-          // operand fetches far less than a bulk (TMA) store of it did (MMA phase 4.4k -> 9.4k cycles).
-          named_bar_sync(1 + g, 128);
-          const int t = int(threadIdx.x & 127);
-          const uint4* src = reinterpret_cast<const uint4*>(a_hi) + t;
-          uint4* dst = reinterpret_cast<uint4*>(h_glob) + t;
-#pragma unroll 8
-          for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
-          named_bar_sync(1 + g, 128);   // all copies done before any warp's next epilogue overwrites the tile
-        }
         if (l == SKIP_LAYER) {
           // E is dead until the next iteration: encode the next tile now, in the shadow of the
           // layer-6/7/heads MMAs.

@@ -7,6 +7,8 @@
 // every persistent CTA owns ONE layer ("role") for the whole launch and streams the [sample x
 // feature] tile images that mlp_fwd (h_l, posenc) and mlp_bwd (dZ_l, dO) left in global memory.
 // Both MMA operands are read MN-major straight from those images (K = samples): no transposes.
+// dZ / dO / posenc tiles are K-major SW128 images (read MN-major with the same swizzle), the h_l tiles
+// are "T" images (no swizzle, 128 B core matrices; tests/test_umma_probe.py pins both conventions).
 // CTAs of the same role split the tiles round-robin and each writes an fp32 partial; reduce_grads
 // (optim.cu) sums the partials into the flat gradient (deterministic, no atomics).
 //
@@ -42,13 +44,17 @@ struct RoleInfo {
   int b_chunks, N;
   int bias_from_b;       // heads: bias = column sums of dO
   int has_bias;
+  int a_t, b_t;          // operand is a forward-saved h tile in the T layout (layouts.py: t_tile_offset)
 };
 
 __device__ __forceinline__ RoleInfo role_info(int role, int NH) {
   RoleInfo r;
   r.bias_from_b = 0;
   r.has_bias = 1;
+  r.a_t = 0;
+  r.b_t = 0;
   if (role < 7) {
+    r.b_t = 1;
     const int l = role < 4 ? role + 1 : (role == 4 ? 5 : role + 1);  // 1,2,3,4,5,6,7
     r.a_kind = 0; r.a_layer = l; r.b_kind = 0; r.b_layer = l - 1; r.b_chunks = 4; r.N = 256;
   } else if (role == 7) {
@@ -58,6 +64,7 @@ __device__ __forceinline__ RoleInfo role_info(int role, int NH) {
   } else {
     r.a_kind = 1; r.a_layer = 7; r.b_kind = 2; r.b_layer = 0; r.b_chunks = (NH + 63) / 64; r.N = NH;
     r.bias_from_b = 1;
+    r.a_t = 1;
   }
   return r;
 }
@@ -189,14 +196,23 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
         if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&bars.full[st]), WG_HALF + b_half_bytes);
           const uint32_t dst = sbase + st * WG_STAGE_BYTES;
+          // SW128 images: 64 rows of each 64-column chunk; T images: two whole 32-row groups (contiguous)
+          if (R.a_t) {
+            bulk_g2s(dst, it.a_ptr + size_t(sub) * WG_HALF, WG_HALF, smem_u32(&bars.full[st]));
+          } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            bulk_g2s(dst + c * (WG_SUB * 128), it.a_ptr + size_t(c) * A_CHUNK_BYTES + sub * (WG_SUB * 128),
-                     WG_SUB * 128, smem_u32(&bars.full[st]));
-          for (int c = 0; c < R.b_chunks; ++c)
-            bulk_g2s(dst + WG_HALF + c * (WG_SUB * 128),
-                     it.b_ptr + size_t(c) * A_CHUNK_BYTES + sub * (WG_SUB * 128), WG_SUB * 128,
-                     smem_u32(&bars.full[st]));
+            for (int c = 0; c < 4; ++c)
+              bulk_g2s(dst + c * (WG_SUB * 128), it.a_ptr + size_t(c) * A_CHUNK_BYTES + sub * (WG_SUB * 128),
+                       WG_SUB * 128, smem_u32(&bars.full[st]));
+          }
+          if (R.b_t) {
+            bulk_g2s(dst + WG_HALF, it.b_ptr + size_t(sub) * WG_HALF, WG_HALF, smem_u32(&bars.full[st]));
+          } else {
+            for (int c = 0; c < R.b_chunks; ++c)
+              bulk_g2s(dst + WG_HALF + c * (WG_SUB * 128),
+                       it.b_ptr + size_t(c) * A_CHUNK_BYTES + sub * (WG_SUB * 128), WG_SUB * 128,
+                       smem_u32(&bars.full[st]));
+          }
         }
         __syncwarp();
         if (++st == WG_STAGES) {
@@ -218,6 +234,8 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
     const uint32_t idesc = make_idesc_f16(128, R.N, 1, 1);
     // MN-major SW128: LBO = stride between 64-feature chunks (8 KB here), SBO = 8-sample group
     constexpr uint64_t DESC_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t((WG_SUB * 128) >> 4) << 16);
+    // MN-major, no swizzle (T images): LBO = next 8 samples = 128 B, SBO = next 8 features = 512 B
+    constexpr uint64_t T_HI = make_sdesc_hi(512, LAYOUT_NONE) | (uint64_t(128 >> 4) << 16);
     bool first = true;
     for (long long i = 0; i < n_items; ++i) {
       const WgItem it = get_item(i);
@@ -229,14 +247,18 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
           // the stage has landed in shared memory: the queue slot may be rewritten by its producer
           if (sub == 1 && it.done_flag) st_release_gpu(it.done_flag, it.done_val);
           const uint32_t a0 = sbase + st * WG_STAGE_BYTES;
-          const uint64_t ad0 = DESC_HI | uint64_t((a0 >> 4) & 0x3FFF);
-          const uint64_t bd0 = DESC_HI | uint64_t(((a0 + WG_HALF) >> 4) & 0x3FFF);
+          const uint64_t ad0 = (R.a_t ? T_HI : DESC_HI) | uint64_t((a0 >> 4) & 0x3FFF);
+          const uint64_t bd0 = (R.b_t ? T_HI : DESC_HI) | uint64_t(((a0 + WG_HALF) >> 4) & 0x3FFF);
 #pragma unroll
           for (int ks = 0; ks < WG_SUB / 16; ++ks) {
             const uint32_t acc = !(first && sub == 0 && ks == 0);
-            // 16 samples = 2048 bytes = +128 encoded; features 128..255 = +2 chunks = +1024 encoded
-            umma_f16(tmem, ad0 + ks * 128, bd0 + ks * 128, idesc, acc);
-            umma_f16(tmem + 256, ad0 + ks * 128 + 1024, bd0 + ks * 128, idesc, acc);
+            // SW128: 16 samples = 2048 bytes = +128 encoded; features 128..255 = +2 chunks = +1024 encoded
+            // T    : 32-sample group = 16 KB = +1024 encoded, 16 samples inside it = 256 B = +16 encoded;
+            //        features 128..255 = 16 units x 512 B = +512 encoded
+            const uint32_t sw_k = uint32_t(ks) * 128u, t_k = uint32_t(ks >> 1) * 1024u + uint32_t(ks & 1) * 16u;
+            const uint64_t ad = ad0 + (R.a_t ? t_k : sw_k), bd = bd0 + (R.b_t ? t_k : sw_k);
+            umma_f16(tmem, ad, bd, idesc, acc);
+            umma_f16(tmem + 256, ad + (R.a_t ? 512u : 1024u), bd, idesc, acc);
           }
           umma_commit(smem_u32(&bars.empty[st]));
         }

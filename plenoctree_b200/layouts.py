@@ -46,6 +46,32 @@ def unpack_a_tile(img, cols):
     return img.view(np.uint16)[off // 2].view(np.float16).astype(np.float32)
 
 
+def t_tile_offset(row, col):
+    """byte offset of fp16 element (row, col) in a "T" tile image: [32-row group][8-column unit]
+    [row in group][16 B].  mlp_fwd writes the saved h_l tiles in this order (one coalesced 512 B
+    store per warp instruction straight from the epilogue registers); read MN-major by the tensor
+    cores it is the canonical no-swizzle layout with 128 B core matrices (8 rows x 8 columns):
+    LBO (next 8 rows) = 128 B, SBO (next 8 columns) = 512 B."""
+    row = np.asarray(row)
+    col = np.asarray(col)
+    return (row >> 5) * 16384 + (col >> 3) * 512 + (row & 31) * 16 + (col & 7) * 2
+
+
+def pack_t_tile(mat):
+    """[128, 256] float -> uint8 image (fp16, T layout)."""
+    rows, cols = mat.shape
+    assert rows == 128 and cols == 256
+    img = np.zeros(rows * cols * 2, dtype=np.uint8)
+    r, c = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    img.view(np.uint16)[t_tile_offset(r, c) // 2] = mat.astype(np.float16).view(np.uint16)
+    return img
+
+
+def unpack_t_tile(img):
+    r, c = np.meshgrid(np.arange(128), np.arange(256), indexing="ij")
+    return img.view(np.uint16)[t_tile_offset(r, c) // 2].view(np.float16).astype(np.float32)
+
+
 def pack_w_slot(mat):
     """[rows, 32] float -> uint8 image (fp16, SW64)."""
     rows, k = mat.shape

@@ -7,7 +7,7 @@ from plenoctree_b200 import ops
 from plenoctree_b200._lib import check, lib, ptr
 flat = O.init_flat_params(3, 1, bias_scale=0.05)
 blob = ops.pack_weights(torch.from_numpy(flat).cuda(), 3)
-m = 148 * 256 * 4
+m = 148 * 256 * int(os.environ.get('TRACE_ITERS', '4'))
 pts = (torch.rand((m, 3), device="cuda") * 3 - 1.5).contiguous()
 sig = torch.empty(m, device="cuda")
 tr = torch.zeros((5, 256), dtype=torch.int64, device="cuda")
@@ -44,6 +44,7 @@ print("slot: issued, observed_full, latency, gap_between_observed")
 for i in range(n):
     print(i, iss[i], obs[i], obs[i] - iss[i], (obs[i] - obs[i-1]) if i else 0)
 print("iteration period (cycles):", mm2[9][0] - mm2[0][0] if len(mm2) > 9 else None)
+print("all iteration periods:", [int(mm2[9*(k+1)][0] - mm2[9*k][0]) for k in range((len(mm2)-1)//9)])
 sys.exit(0)
 print("epi stamps per trunk layer: [d_ready, drained, signalled]  (heads epilogue has no stamps)")
 print("layer-step | MMA a_rdyX a_rdyY issued | epiX d_ready drained signalled | epiY d_ready drained signalled")

@@ -112,3 +112,71 @@ def test_mn_major_sw128_wgrad_operands():
         errs[name] = _mn_major_case(lbo, sbo)
     _record("mn_major", errs)
     assert errs["lbo_chunk_sbo_1024"] < 1e-5, errs
+
+
+def _t_layout_case(lbo, sbo, h_is_b):
+    """weight-gradient contraction with the forward-saved h tile in the T layout (no swizzle, MN-major)
+    on one side and a SW128 dZ tile on the other, 64 samples per stage like mlp_wgrad."""
+    from plenoctree_b200 import layouts as L, ops
+    rs = np.random.RandomState(3)
+    DZ = _f16(rs.normal(size=(128, 256)))
+    H = _f16(rs.normal(size=(128, 256)))
+    sw_img = L.pack_a_tile(DZ)
+    t_img = L.pack_t_tile(H)
+    off2 = 65536
+    ad, bd, dc, ac = [], [], [], []
+    for half in range(2):
+        for ks in range(8):  # 16 samples per MMA
+            sw = L.make_sdesc(half * 2 * L.A_CHUNK_BYTES + ks * 2048, 16384, 1024, L.LAYOUT_SW128)
+            # T image: 32-sample group ks>>1 (16 KB), 16-sample half (ks&1) = two 128 B core matrices
+            tt = L.make_sdesc(off2 + (ks >> 1) * 16384 + (ks & 1) * 256, lbo, sbo, L.LAYOUT_NONE)
+            if h_is_b:
+                ad.append(sw)
+                bd.append(tt)
+            else:   # heads role: A = h (features 128*half ..), B = the SW128 tile
+                ad.append(L.make_sdesc(off2 + (ks >> 1) * 16384 + (ks & 1) * 256 + half * 16 * sbo, lbo, sbo, L.LAYOUT_NONE) if sbo == 512
+                          else L.make_sdesc(off2 + (ks >> 1) * 16384 + (ks & 1) * 256 + half * 16 * lbo, lbo, sbo, L.LAYOUT_NONE))
+                bd.append(L.make_sdesc(ks * 2048, 16384, 1024, L.LAYOUT_SW128))
+            dc.append(256 * half)
+            ac.append(0 if ks == 0 else 1)
+    idesc = L.make_idesc_f16(128, 256, a_mn_major=1, b_mn_major=1)
+    got = ops.umma_probe(sw_img, t_img, off2, ad, bd, dc, ac, idesc, 512)
+    want = (DZ.T @ H) if h_is_b else (H.T @ DZ)
+    return max(_relerr(got[:, :256], want[:128]), _relerr(got[:, 256:], want[128:]))
+
+
+def test_mn_major_t_layout_wgrad_operands():
+    errs = {}
+    for name, (lbo, sbo) in {"lbo128_sbo512": (128, 512), "lbo512_sbo128": (512, 128)}.items():
+        errs[name + "_b"] = _t_layout_case(lbo, sbo, True)
+        errs[name + "_a"] = _t_layout_case(lbo, sbo, False)
+    _record("mn_major_t_layout", errs)
+    ok = [k[:-2] for k in errs if errs[k] < 1e-5]
+    assert any(ok.count(n) == 2 for n in ok), errs
+
+
+def test_cta_pair_kmajor_weight_halves():
+    """cta_group::2 (M = 256 over a CTA pair): each CTA stages its own 128 activation rows (K-major SW128)
+    and HALF of the weight rows of every slot (K-major SW64: rows 128r..128r+127 = bytes [8192r, +8192) of
+    a 16 KB slot); both CTAs receive all N accumulator columns for their rows."""
+    from plenoctree_b200 import layouts as L, ops
+    rs = np.random.RandomState(4)
+    for N in (256, 64, 80):
+        A = _f16(rs.normal(size=(256, 64)))
+        B = _f16(rs.normal(size=(N, 64)))
+        a_img = np.stack([L.pack_a_tile(A[:128]), L.pack_a_tile(A[128:])])
+        hb = N // 2 * 64  # bytes of one CTA's half of a slot
+        slots = [L.pack_w_slot(B[:, 0:32]), L.pack_w_slot(B[:, 32:64])]
+        b_img = np.stack([np.concatenate([s[r * hb:(r + 1) * hb] for s in slots]) for r in range(2)])
+        b_off = 16384
+        ad, bd, dc, ac = [], [], [], []
+        for j in range(2):
+            for ks in range(2):
+                ad.append(L.make_sdesc(j * 64 + ks * 32, 16, 1024, L.LAYOUT_SW128))
+                bd.append(L.make_sdesc(b_off + j * hb + ks * 32, 16, 512, L.LAYOUT_SW64))
+                dc.append(0)
+                ac.append(0 if (j | ks) == 0 else 1)
+        got = ops.umma_probe(a_img, b_img, b_off, ad, bd, dc, ac, L.make_idesc_f16(256, N), N, pair=True)
+        err = _relerr(got, A @ B.T)
+        _record(f"pair_kmajor_N{N}", err)
+        assert err < 1e-5, f"N={N} rel err {err}"
