@@ -185,6 +185,92 @@ int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_
                         void* save_e_dev, void* save_mask_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * PlenOctree side.  These entry points stand where the
+ * reference calls the third-party `svox` extension (absent from the reference tree; the oracle
+ * restates its published algorithm, parity unpinned — see oracle/octree_oracle.py):
+ *   svox.N3Tree / N3TreeView          octree/extraction.py:330-394,489-509
+ *   svox.VolumeRenderer.render_persp  octree/optimization.py:174-229, octree/nerf/utils.py:448-498
+ *   svox _C.grid_weight_render        octree/extraction.py:181-214
+ * Tree layout (svox N3Tree, keys of tree.npz: octree/compression.py:75-95):
+ *   data  [n_nodes, N, N, N, data_dim] fp32, sigma is the LAST channel (octree/extraction.py:391),
+ *         SH coefficients channel-major c*K + k before it (same order as raw_rgb of eval_points_raw);
+ *   child [n_nodes, N, N, N] int32: index of the child node minus the index of this node, 0 = leaf;
+ *   world -> tree coordinates: p * invradius + offset in [0,1]^3.
+ * ------------------------------------------------------------------------------------------- */
+#define POB_OCTREE_RGBA 0 /* data_dim 4: colour = sigmoid(data[0:3])                              */
+#define POB_OCTREE_SH 1   /* data_dim 3K+1: colour = sigmoid(sum_k Y_k(viewdir) * data[c*K+k])    */
+
+typedef struct pob_octree {
+  const float* data_dev;
+  const int32_t* child_dev;
+  int64_t n_nodes;
+  int N;          /* branch factor per axis (flag tree_branch_n, octree/extraction.py:100) */
+  int data_dim;
+  int basis_dim;  /* K */
+  int format;     /* POB_OCTREE_* */
+  float offset[3];
+  float invradius[3];
+} pob_octree;
+
+/* svox RenderOptions as VolumeRenderer fills them: step_size = flag renderer_step_size
+ * (octree/nerf/utils.py:211-215), background_brightness 1, and sigma_thresh = stop_thresh = 1e-2 when
+ * fast=True (evaluation without --no_early_stop, octree/nerf/utils.py:472), 0 otherwise. */
+typedef struct pob_octree_opts {
+  float step_size;
+  float background_brightness;
+  float sigma_thresh;
+  float stop_thresh;
+} pob_octree_opts;
+
+/* perspective camera: c2w = first three rows of the camera-to-world matrix, row-major [3][4]
+ * (svox CameraSpec: octree/extraction.py:194-199).  16 floats, also the element type of camera arrays. */
+typedef struct pob_camera {
+  float c2w[12];
+  float fx, fy;
+  float width, height;
+} pob_camera;
+
+/* VolumeRenderer.forward(rays) / render_persp(c2w, width, height, fx): composite the tree along rays.
+ * Either explicit rays (origins/dirs/vdirs [n_rays,3], cam NULL) or a pixel-row slab [row0, row0+nrows) of a
+ * perspective camera (cam != NULL, ray pointers ignored; out is [nrows*width, 3] row-major).
+ * counters_dev (may be NULL): [2] += {leaf visits, contributing leaf visits} for the roofline accounting. */
+int pob_octree_render(const pob_octree* tree, const pob_octree_opts* opts, const float* origins_dev,
+                      const float* dirs_dev, const float* vdirs_dev, int64_t n_rays, const pob_camera* cam,
+                      int row0, int nrows, float* out_rgb_dev, unsigned long long* counters_dev, void* stream);
+
+/* reverse mode of the above for an upstream gradient grad_out [n,3]: grad_data_dev (same shape as data,
+ * ACCUMULATED into) += d<grad_out, rgb>/d data.  Thresholds are ignored like in svox's backward. */
+int pob_octree_render_backward(const pob_octree* tree, const pob_octree_opts* opts, const float* origins_dev,
+                               const float* dirs_dev, const float* vdirs_dev, int64_t n_rays, const pob_camera* cam,
+                               int row0, int nrows, const float* grad_out_dev, float* grad_data_dev, void* stream);
+
+/* One training image of octree.optimization (octree/optimization.py:201-207) in one launch:
+ *   im = render_persp(c2w); mse = mean((clamp(im,0,1) - gt)^2); mse.backward()
+ * over the pixel rows [row0,row0+nrows): grad_data += grad_scale * d sum((clamp(im)-gt)^2) / d data,
+ * *sq_err_sum_dev += sum((clamp(im)-gt)^2)  (grad_scale = 1/(H*W*3) gives the reference's mean);
+ * gt_rgb_dev [nrows*width,3]; out_rgb_dev (may be NULL) receives the rendered slab. */
+int pob_octree_train_persp(const pob_octree* tree, const pob_octree_opts* opts, const pob_camera* cam, int row0,
+                           int nrows, const float* gt_rgb_dev, float grad_scale, float* grad_data_dev,
+                           double* sq_err_sum_dev, float* out_rgb_dev, void* stream);
+
+/* torch.optim.SGD(lr, momentum 0).step() fused with zero_grad (octree/optimization.py:187-189,205-208):
+ * data -= lr * grad; grad = 0, touching only entries whose gradient is non-zero. */
+int pob_octree_sgd_step(float* data_dev, float* grad_dev, int64_t n, float lr, void* stream);
+
+/* N3Tree.__getitem__(points): packed leaf index node*N^3 + (i*N + j)*N + k of the leaf holding each world
+ * point (points clamped into the volume like svox). */
+int pob_octree_query(const pob_octree* tree, const float* points_dev, int64_t n, int64_t* leaf_index_dev,
+                     void* stream);
+
+/* calculate_grid_weights (octree/extraction.py:181-214): march all pixels of n_cams cameras (cams_dev: device
+ * array of pob_camera) through the dense sigma grid [reso]^3 and max-accumulate the per-voxel compositing
+ * weight into max_weight_dev (caller zero-initialises; all cameras in one launch, no per-camera grids).
+ * hit_dev (may be NULL): uint8 [reso]^3 set to 1 where any ray contributed. */
+int pob_grid_weight_render(const float* sigma_grid_dev, int reso, const pob_camera* cams_dev, int n_cams,
+                           int max_width, int max_height, const float offset[3], const float invradius[3],
+                           const pob_octree_opts* opts, float* max_weight_dev, uint8_t* hit_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Test bench for the tcgen05 descriptor conventions (tests/test_umma_probe.py).
  * Runs `nops` tcgen05.mma (kind::f16, M=128) on two shared-memory images and returns the
  * [128 x out_cols] fp32 accumulator.

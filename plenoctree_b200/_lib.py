@@ -44,6 +44,13 @@ SIGNATURES = {
     "pob_debug_bwdw_stalls": (_i, [_vp, _vp, _vp]),
     "pob_adam_update": (_i, [_i, _i, _fp, _fp, _fp, _fp, _c.c_float, _c.c_float, _c.c_float, _c.c_float,
                              _vp, _vp, _vp]),
+    "pob_octree_render": (_i, [_vp, _vp, _fp, _fp, _fp, _i64, _vp, _i, _i, _fp, _vp, _vp]),
+    "pob_octree_render_backward": (_i, [_vp, _vp, _fp, _fp, _fp, _i64, _vp, _i, _i, _fp, _fp, _vp]),
+    "pob_octree_train_persp": (_i, [_vp, _vp, _vp, _i, _i, _fp, _c.c_float, _fp, _vp, _fp, _vp]),
+    "pob_octree_sgd_step": (_i, [_fp, _fp, _i64, _c.c_float, _vp]),
+    "pob_octree_query": (_i, [_vp, _fp, _i64, _vp, _vp]),
+    "pob_grid_weight_render": (_i, [_fp, _i, _vp, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
+                                    _vp, _fp, _vp, _vp]),
     "pob_umma_probe": (_i, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i, _u32, _i, _fp, _vp]),
     "pob_umma_probe_pair": (_i, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i, _u32, _i, _fp, _vp]),
 }
@@ -56,6 +63,21 @@ class RenderConfig(_c.Structure):
 
 class TrainHParams(_c.Structure):
     _fields_ = [("sparsity_weight", _c.c_float), ("sparsity_length", _c.c_float), ("loss_scale", _c.c_float)]
+
+
+class Octree(_c.Structure):
+    _fields_ = [("data_dev", _vp), ("child_dev", _vp), ("n_nodes", _i64), ("N", _i), ("data_dim", _i),
+                ("basis_dim", _i), ("format", _i), ("offset", _c.c_float * 3), ("invradius", _c.c_float * 3)]
+
+
+class OctreeOpts(_c.Structure):
+    _fields_ = [("step_size", _c.c_float), ("background_brightness", _c.c_float), ("sigma_thresh", _c.c_float),
+                ("stop_thresh", _c.c_float)]
+
+
+class Camera(_c.Structure):
+    _fields_ = [("c2w", _c.c_float * 12), ("fx", _c.c_float), ("fy", _c.c_float), ("width", _c.c_float),
+                ("height", _c.c_float)]
 
 
 class PobError(RuntimeError):

@@ -33,9 +33,13 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in heads)
 
 
+# per-file extras: the octree march must round like its float32 oracle (no FMA contraction; HBM/latency bound)
+EXTRA = {"octree.cu": ["--fmad=false"]}
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

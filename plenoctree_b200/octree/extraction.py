@@ -1,0 +1,184 @@
+"""Host-side mirror of `octree/extraction.py` (NeRF-SH -> PlenOctree conversion) over the CUDA library.
+
+    reference                                        here
+    calculate_grid_weights   extraction.py:181-214   calculate_grid_weights  (all cameras in one launch)
+    auto_scale               extraction.py:244-286   auto_scale              (pob_eval_grid: no host grid)
+    step1                    extraction.py:288-353   step1
+    step2                    extraction.py:355-394   step2                   (pob_eval_cells_mean epilogue)
+    main                     extraction.py:425-516   extract                 (flags arrive as an args namespace)
+
+`args` carries the reference's flag names (extraction.py:66-176, octree/nerf/utils.py:60-253); `default_args()`
+returns the reference defaults.  `nerf` is plenoctree_b200.nerf.models.NerfModel; `dataset` needs .w .h .focal
+.camtoworlds [n,4,4] (and .size), like octree/nerf/datasets.py.  Vanilla-NeRF SH projection, SG and NDC/LLFF are
+outside the scope of this path and raise NotImplementedError.
+"""
+import ctypes
+import math
+import types
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .._lib import check, lib, ptr, stream_ptr
+from .n3tree import N3Tree
+from .renderer import camera_array
+
+
+def default_args(**kw):
+    a = types.SimpleNamespace(
+        output="./tree.npz", center="0 0 0", radius="1.5", alpha_thresh=0.01, max_refine_prop=0.5, z_min=None,
+        z_max=None, tree_branch_n=2, init_grid_depth=8, samples_per_cell=8, is_jaxnerf_ckpt=False,
+        masking_mode="weight", weight_thresh=0.001, projection_samples=10000, bbox_from_data=False,
+        data_bbox_scale=1.0, autoscale=False, bbox_cube=False, bbox_scale=1.0, scale_alpha_thresh=0.01, eval=True,
+        chunk=81920, renderer_step_size=1e-4, sh_deg=3, sg_dim=-1, use_viewdirs=False, num_rgb_channels=3,
+        config="", spherify=False, no_early_stop=False)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _grid_sigmas(nerf, reso, offset, scale, world=1, rank=0):
+    """the chunked eval_points_raw loop over the dense grid (extraction.py:262-274 / 308-320) as one sweep whose
+    voxel centres are generated in the kernel; returns sigma [reso^3] x-major (this rank's x-slab when world > 1)."""
+    x0, nx = ops.grid_slab(reso, rank, world)
+    _, sig = ops.eval_grid(nerf._blob(False), nerf.sh_deg, reso, offset, scale, x0=x0, nx=nx, want_rgb=False,
+                           precision=nerf.precision, device=nerf.device)
+    return sig
+
+
+def calculate_grid_weights(dataset, sigmas, reso, invradius, offset, step_size=1e-4, cam_chunk=4096):
+    """extraction.py:181-214.  One launch marches the rays of every training camera through the grid and keeps the
+    per-voxel maximum weight directly (atomic max); the reference renders one weight grid per camera and reduces
+    with torch.max."""
+    dev = sigmas.device
+    grid = sigmas.reshape(reso, reso, reso).contiguous().float()
+    wmax = torch.zeros_like(grid)
+    c2ws = np.asarray(dataset.camtoworlds, dtype=np.float32)
+    cams = camera_array(c2ws, dataset.w, dataset.h, dataset.focal, device=dev)
+    o = _lib.OctreeOpts()
+    o.step_size = float(step_size)
+    o.background_brightness = 1.0
+    o.sigma_thresh = 0.0
+    o.stop_thresh = 0.0
+    off = (ctypes.c_float * 3)(*[float(v) for v in offset.detach().cpu().numpy().reshape(3)])
+    inv = (ctypes.c_float * 3)(*[float(v) for v in invradius.detach().cpu().numpy().reshape(3)])
+    for c0 in range(0, cams.shape[0], cam_chunk):
+        sub = cams[c0:c0 + cam_chunk].contiguous()
+        check(lib.pob_grid_weight_render(ptr(grid), reso, ptr(sub), sub.shape[0], int(dataset.w), int(dataset.h), off,
+                                         inv, ctypes.byref(o), ptr(wmax), None, stream_ptr()))
+    return wmax
+
+
+def _axes(reso, offset, scale, dev):
+    arr = (torch.arange(0, reso, dtype=torch.float32, device=dev) + 0.5) / reso
+    return [(arr - offset[a]) / scale[a] for a in range(3)]
+
+
+def auto_scale(args, center, radius, nerf):
+    """extraction.py:244-286: bounding box of the voxels whose sigma passes scale_alpha_thresh."""
+    if args.z_min is not None or args.z_max is not None:
+        raise NotImplementedError("z_min / z_max (NDC scenes) are outside the scope of this path")
+    reso = 2 ** args.init_grid_depth
+    radius = torch.tensor(radius, dtype=torch.float32)
+    center = torch.tensor(center, dtype=torch.float32)
+    scale = 0.5 / radius
+    offset = 0.5 * (1.0 - center / radius)
+    sigmas = _grid_sigmas(nerf, reso, offset.tolist(), scale.tolist())
+    approx_delta = 2.0 / reso
+    sigma_thresh = -np.log(1.0 - args.scale_alpha_thresh) / approx_delta
+    mask = (sigmas >= sigma_thresh).reshape(reso, reso, reso)
+    xx, yy, zz = _axes(reso, offset.to(sigmas.device), scale.to(sigmas.device), sigmas.device)
+    lc, uc = [], []
+    for a, ax in enumerate((xx, yy, zz)):
+        occ = mask.any(dim=tuple(d for d in range(3) if d != a))
+        vals = ax[occ]
+        lc.append(float(vals.min()) - 0.5 / reso)
+        uc.append(float(vals.max()) + 0.5 / reso)
+    lc, uc = np.asarray(lc, dtype=np.float32), np.asarray(uc, dtype=np.float32)
+    return ((lc + uc) * 0.5).tolist(), ((uc - lc) * 0.5).tolist()
+
+
+def step1(args, tree, nerf, dataset, refine_chunk=2000000):
+    """extraction.py:288-353: dense sigma grid -> mask (sigma or weight) -> level-by-level refinement."""
+    if args.z_min is not None or args.z_max is not None:
+        raise NotImplementedError("z_min / z_max (NDC scenes) are outside the scope of this path")
+    reso = 2 ** (args.init_grid_depth + 1)
+    offset, scale = tree.offset, tree.invradius
+    approx_delta = 2.0 / reso
+    sigma_thresh = -np.log(1.0 - args.alpha_thresh) / approx_delta
+    sigmas = _grid_sigmas(nerf, reso, offset.tolist(), scale.tolist())
+    if args.masking_mode == "sigma":
+        mask = sigmas >= sigma_thresh
+    elif args.masking_mode == "weight":
+        grid_weights = calculate_grid_weights(dataset, sigmas, reso, tree.invradius, tree.offset,
+                                              step_size=args.renderer_step_size)
+        mask = grid_weights.reshape(-1) >= args.weight_thresh
+        del grid_weights
+    else:
+        raise ValueError
+    del sigmas
+    idx = torch.nonzero(mask.reshape(reso, reso, reso))  # x-major order == grid[mask] of the reference
+    del mask
+    xx, yy, zz = _axes(reso, offset, scale, tree.device)
+    grid = torch.stack([xx[idx[:, 0]], yy[idx[:, 1]], zz[idx[:, 2]]], dim=1).contiguous()
+    for _ in range(args.init_grid_depth - 1):
+        tree[grid].refine()
+    if grid.shape[0] <= refine_chunk:
+        tree[grid].refine()
+    else:
+        for j in range(0, grid.shape[0], refine_chunk):
+            tree[grid[j:j + refine_chunk]].refine()
+    assert tree.max_depth == args.init_grid_depth
+    return grid
+
+
+def step2(args, tree, nerf, cells_per_launch=None):
+    """extraction.py:355-394 (SH data formats): S uniform samples per finest leaf, mean of [raw_rgb, raw_sigma].
+    The per-cell mean is taken in the MLP kernel's epilogue (pob_eval_cells_mean); launches cover
+    `cells_per_launch` leaves (default: 2^22 points) instead of chunk // S = 320."""
+    if args.use_viewdirs:
+        raise NotImplementedError("vanilla-NeRF SH projection (use_viewdirs) is outside the scope of this path")
+    if tree.data_format.format != 1:
+        raise NotImplementedError("step 2 is implemented for SH trees (the RGBA alpha-weighted mean is not built)")
+    S = int(args.samples_per_cell)
+    leaf_ind = torch.where(tree.depths == tree.max_depth)[0]
+    if cells_per_launch is None:
+        cells_per_launch = max(1, (1 << 22) // S)
+    for i in range(0, leaf_ind.shape[0], cells_per_launch):
+        chunk_inds = leaf_ind[i:i + cells_per_launch]
+        points = tree[chunk_inds].sample(S)
+        rgba = ops.eval_cells_mean(nerf._blob(False), nerf.sh_deg, points.contiguous(), S, precision=nerf.precision)
+        tree[chunk_inds] = rgba
+
+
+def extract(args, nerf, dataset):
+    """extraction.py:425-509 without file/flag plumbing: returns the N3Tree (saved to args.output if set)."""
+    if args.sg_dim > 0:
+        raise NotImplementedError("SG trees are outside the scope of this path")
+    data_format = f"SH{(args.sh_deg + 1) ** 2}" if args.sh_deg > 0 else None
+    center = list(map(float, str(args.center).split()))
+    if len(center) == 1:
+        center *= 3
+    radius = list(map(float, str(args.radius).split()))
+    if len(radius) == 1:
+        radius *= 3
+    if args.autoscale:
+        center, radius = auto_scale(args, center, radius, nerf)
+    radius = [r * args.bbox_scale for r in radius]
+    if args.bbox_cube:
+        radius = [max(radius)] * 3
+    num_rgb_channels = args.num_rgb_channels
+    if args.sh_deg >= 0:
+        num_rgb_channels *= (args.sh_deg + 1) ** 2
+    data_dim = 1 + num_rgb_channels
+    tree = N3Tree(N=args.tree_branch_n, data_dim=data_dim, init_refine=0, init_reserve=500000, geom_resize_fact=1.0,
+                  depth_limit=args.init_grid_depth, radius=radius, center=center, data_format=data_format,
+                  map_location=nerf.device)
+    step1(args, tree, nerf, dataset)
+    step2(args, tree, nerf)
+    tree[:, -1:].relu_()
+    tree.shrink_to_fit()
+    if args.output:
+        tree.save(args.output, compress=False)
+    return tree

@@ -1,0 +1,98 @@
+"""Host-side mirror of `octree/optimization.py` (direct PlenOctree fine-tuning on the training images).
+
+    reference                                             here
+    run_test_step          optimization.py:191-209        run_test_step
+    epoch loop             optimization.py:213-243        optimize  (SGD path: one fused launch per image +
+                                                          pob_octree_sgd_step; no autograd graph)
+    svox.N3Tree.load/save  optimization.py:168,245-248    plenoctree_b200.octree.N3Tree
+
+Multi-GPU: every image's pixel rows are split over the ranks, each rank scatters into its own
+dense gradient buffer, one NCCL all-reduce (SUM) per image joins them before the replicated SGD update.  The
+Adam branch of the reference (`--nosgd`) is not built (the shipped configs all use --sgd, octree/config/*.json).
+"""
+import math
+import types
+
+import numpy as np
+import torch
+
+from .n3tree import N3Tree
+from .renderer import VolumeRenderer
+
+
+def default_args(**kw):
+    a = types.SimpleNamespace(input="./tree.npz", output="./tree_opt.npz", render_interval=0, val_interval=2,
+                              num_epochs=80, sgd=True, lr=1e7, sgd_momentum=0.0, sgd_nesterov=False,
+                              nosave=False, continue_on_decrease=False, renderer_step_size=1e-4)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def row_slab(height, rank, world):
+    base, rem = divmod(height, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, base + (1 if rank < rem else 0)
+
+
+def run_test_step(r, test_c2w, test_gt, H, W, focal):
+    """optimization.py:191-209: mean PSNR of full-quality renders (fast=False) over the validation images."""
+    tpsnr = 0.0
+    with torch.no_grad():
+        for c2w, im_gt in zip(test_c2w, test_gt):
+            im = r.render_persp(c2w, height=H, width=W, fx=focal, fast=False).clamp_(0.0, 1.0)
+            mse = ((im - im_gt.to(im.device)) ** 2).mean()
+            tpsnr += -10.0 * math.log10(float(mse))
+    return tpsnr / max(len(test_c2w), 1)
+
+
+def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr):
+    """one pass over the training images (optimization.py:216-229); returns the mean train PSNR."""
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    rows = row_slab(H, rank, world)
+    sq = torch.zeros(len(train_c2w), dtype=torch.float64, device=tree.device)
+    for j, (c2w, im_gt) in enumerate(zip(train_c2w, train_gt)):
+        r.train_persp(c2w, im_gt, W, H, focal, rows=rows if world > 1 else None, sq_err=sq[j:j + 1])
+        if world > 1:
+            dist.all_reduce(tree.grad_buffer()[:tree.n_internal])
+        tree.sgd_step(lr)
+    if world > 1:
+        dist.all_reduce(sq)
+    mse = (sq / float(H * W * 3)).cpu().numpy()
+    return float(np.mean(-10.0 * np.log10(mse)))
+
+
+def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=print):
+    """optimization.py:134-248 without dataset/flag plumbing.  train_gt/test_gt: [n,H,W,3] float tensors."""
+    if not args.sgd:
+        raise NotImplementedError("the Adam branch of octree.optimization is not built")
+    if args.sgd_momentum != 0.0 or args.sgd_nesterov:
+        raise NotImplementedError("SGD momentum is not built (reference configs use momentum 0)")
+    H, W = int(train_gt[0].shape[0]), int(train_gt[0].shape[1])
+    r = VolumeRenderer(tree, step_size=args.renderer_step_size)
+    best_validation_psnr = run_test_step(r, test_c2w, test_gt, H, W, focal)
+    log(f"** initial val psnr {best_validation_psnr}")
+    best_t = None
+    for i in range(args.num_epochs):
+        tpsnr = train_epoch(tree, r, train_c2w, train_gt, H, W, focal, args.lr)
+        log(f"** train_psnr {tpsnr}")
+        if i % args.val_interval == args.val_interval - 1 or i == args.num_epochs - 1:
+            validation_psnr = run_test_step(r, test_c2w, test_gt, H, W, focal)
+            log(f"** val psnr {validation_psnr} best {best_validation_psnr}")
+            if validation_psnr > best_validation_psnr:
+                best_validation_psnr = validation_psnr
+                best_t = tree.clone()
+            elif not args.continue_on_decrease:
+                log("Stop since overfitting")
+                break
+    if not args.nosave and best_t is not None and args.output:
+        best_t.save(args.output, compress=False)
+    return best_t, best_validation_psnr
