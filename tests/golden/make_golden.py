@@ -118,7 +118,62 @@ if __name__ == "__main__":
     gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
     gen_eval_sh()
     gen_posenc()
+    gen_ckpt_bridge()
     try:
         gen_rays()
     except Exception as e:  # octree/nerf/utils.py pulls optional deps
         print("rays.npz skipped:", repr(e))
+
+
+def gen_ckpt_bridge():
+    """Let the REFERENCE's own loader (octree/nerf/models.py:66-113 restore_model_state_from_jaxnerf) consume a
+    flax-format checkpoint written by plenoctree_b200.nerf.checkpoints.  flax is not installed, so the one call the
+    loader makes into it (flax.training.checkpoints.restore_checkpoint(train_dir, target=None)) is served by this
+    package's msgpack reader; everything after that — key names, Dense index mapping, transposes, load_state_dict
+    into the reference torch model, eval_points_raw — is reference code."""
+    import hashlib
+    import tempfile
+    import types
+    from octree.nerf import models as ref_models
+    from plenoctree_b200.nerf import checkpoints as C
+    sh_deg = 3
+    flat_c = O.init_flat_params(sh_deg, 4101, bias_scale=0.05)
+    flat_f = O.init_flat_params(sh_deg, 4102, bias_scale=0.05)
+    flat = np.concatenate([flat_c, flat_f])
+    rs = np.random.RandomState(4103)
+    m = rs.normal(size=flat.shape).astype(np.float32) * 1e-3
+    v = (rs.uniform(size=flat.shape).astype(np.float32) * 1e-6)
+    step = 12345
+    blob = C.msgpack_serialize(C.train_state_dict(flat, m, v, step, sh_deg))
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, f"checkpoint_{step}"), "wb") as f:
+        f.write(blob)
+    fake_flax = types.ModuleType("flax")
+    fake_training = types.ModuleType("flax.training")
+    fake_ckpt = types.ModuleType("flax.training.checkpoints")
+    fake_ckpt.restore_checkpoint = lambda train_dir, target=None: C.restore_flax_state_dict(train_dir)
+    fake_training.checkpoints = fake_ckpt
+    fake_flax.training = fake_training
+    sys.modules.update({"flax": fake_flax, "flax.training": fake_training, "flax.training.checkpoints": fake_ckpt})
+    try:
+        model = ref_models.NerfModel(use_viewdirs=False, sh_deg=sh_deg, num_rgb_channels=3 * 16,
+                                     num_coarse_samples=64, num_fine_samples=128)
+        args = types.SimpleNamespace(train_dir=tmp)
+        model = ref_models.restore_model_state_from_jaxnerf(args, model).eval()
+    finally:
+        for k in ("flax", "flax.training", "flax.training.checkpoints"):
+            sys.modules.pop(k, None)
+    pts = rs.uniform(-1.5, 1.5, size=(64, 3)).astype(np.float32)
+    with torch.no_grad():
+        rgb_f, sig_f = model.eval_points_raw(torch.from_numpy(pts))
+        rgb_c, sig_c = model.eval_points_raw(torch.from_numpy(pts), coarse=True)
+    sd = model.state_dict()
+    keys = sorted(sd.keys())
+    np.savez_compressed(os.path.join(HERE, "ckpt_bridge.npz"), sh_deg=sh_deg, seeds=np.array([4101, 4102, 4103]),
+                        step=step, sha256=hashlib.sha256(blob).hexdigest(), nbytes=len(blob), points=pts,
+                        raw_rgb_fine=rgb_f.numpy(), raw_sigma_fine=sig_f.numpy(), raw_rgb_coarse=rgb_c.numpy(),
+                        raw_sigma_coarse=sig_c.numpy(), keys=np.array(keys),
+                        shapes=np.array([";".join(map(str, sd[k].shape)) for k in keys]),
+                        sums=np.array([float(sd[k].double().sum()) for k in keys]),
+                        abs_sums=np.array([float(sd[k].double().abs().sum()) for k in keys]))
+    print("ckpt_bridge.npz", len(keys), "tensors,", len(blob), "bytes")
