@@ -151,7 +151,109 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- leaf lookup with a per-ray path cache --------------------------------------------------------------
+// Consecutive samples of a ray fall into neighbouring leaves that share most of their ancestors, yet svox walks
+// down from the root for every sample (depth x dependent L2 loads).  For N = 2 the cell digits of a point are the
+// binary digits of its coordinates (x*2 and x - floor(x) are exact in fp32), so the walk can resume below the deepest
+// ancestor shared with the previous sample: lane k of the group keeps the node entered at level k (the otherwise
+// idle lanes are the stack), the shared depth is a count-leading-zeros of the XOR of the integer coordinates, and
+// the position inside the leaf is frac(x * 2^(depth+1)) — bit-identical to the iterated form.  Other branch
+// factors, and levels deeper than 22, use the plain walk.
+template <int G>
+struct Marcher {
+  unsigned pq0, pq1, pq2;
+  int pdepth;   // depth of the previous leaf, -1 = no previous sample
+  int path;     // lane k: node entered at level k (lane 0: root)
+
+  __device__ __forceinline__ void init() {
+    pdepth = -1;
+    path = 0;
+    pq0 = pq1 = pq2 = 0;
+  }
+
+  // leaf holding origin + t * dir; returns its flat index and the march length to its exit (+ step)
+  __device__ __forceinline__ long long locate(const TreeDev& T, const Ray& r, float step, float t, int l, unsigned mask,
+                                              float& delta_t) {
+    float pos[3], cube;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) pos[a] = r.o[a] + t * r.d[a];
+    long long idx;
+    if (T.N == 2) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pos[a] = fmaxf(0.0f, fminf(1.0f - 1e-6f, pos[a]));
+      const unsigned q0 = __float2uint_rz(pos[0] * 8388608.0f);
+      const unsigned q1 = __float2uint_rz(pos[1] * 8388608.0f);
+      const unsigned q2 = __float2uint_rz(pos[2] * 8388608.0f);
+      int s = 0, node = 0;
+      if (pdepth >= 0) {
+        const unsigned diff = (q0 ^ pq0) | (q1 ^ pq1) | (q2 ^ pq2);
+        const int c = diff ? __clz(int(diff << 9)) : 23;
+        s = min(min(c, pdepth), G - 1);
+        node = __shfl_sync(mask, path, s, G);
+      }
+      pq0 = q0;
+      pq1 = q1;
+      pq2 = q2;
+      int k = s;
+      idx = 0;
+      bool leaf = false;
+      for (; k <= 22; ++k) {
+        const int sh = 22 - k;
+        idx = (long long)node * 8 + ((((q0 >> sh) & 1u) << 2) | (((q1 >> sh) & 1u) << 1) | ((q2 >> sh) & 1u));
+        const int skip = __ldg(T.child + idx);
+        if (skip == 0) {
+          leaf = true;
+          break;
+        }
+        node += skip;
+        if (l == k + 1) path = node;
+      }
+      if (leaf) {
+        pdepth = k;
+        cube = __int_as_float((127 + k + 1) << 23);  // 2^(k+1)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float sc = pos[a] * cube;
+          pos[a] = sc - floorf(sc);
+        }
+      } else {
+        // deeper than the 23 cached digits: finish with the plain walk from `node`
+        pdepth = 22;
+        cube = 8388608.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float sc = pos[a] * cube;
+          pos[a] = sc - floorf(sc);
+        }
+        for (int level = 23; level < MAX_TREE_DEPTH; ++level) {
+          int u[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            pos[a] = pos[a] * 2.0f;
+            const float fl = floorf(pos[a]);
+            u[a] = int(fl);
+            pos[a] = pos[a] - fl;
+          }
+          cube = cube * 2.0f;
+          idx = (long long)node * 8 + (u[0] * 4 + u[1] * 2 + u[2]);
+          const int skip = __ldg(T.child + idx);
+          if (skip == 0) break;
+          node += skip;
+        }
+      }
+    } else {
+      idx = query_leaf(T.child, T.N, pos, cube);
+    }
+    float smin, smax;
+    dda_unit(pos, r.invd, smin, smax);
+    delta_t = (smax - smin) / cube + step;
+    return idx;
+  }
+};
+
 // ---- forward march of one ray by one lane group -------------------------------------------------------
+// Software-pipelined: the loads of the current leaf (sigma and this lane's three coefficients, issued
+// unconditionally) are in flight while the next leaf is located; the march itself never depends on the data.
 template <int G>
 __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, const Ray& r, float basis_l, int l,
                                               unsigned mask, float* out, unsigned& visits, unsigned& hits) {
@@ -163,31 +265,36 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
   float light = 1.0f;
   float t = r.tmin;
   const int K = T.K, D = T.D;
-  for (int it = 0; t < r.tmax && it < MAX_MARCH_STEPS; ++it) {
-    float pos[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) pos[a] = r.o[a] + t * r.d[a];
-    float cube;
-    const long long idx = query_leaf(T.child, T.N, pos, cube);
-    float smin, smax;
-    dda_unit(pos, r.invd, smin, smax);
-    const float delta_t = (smax - smin) / cube + O.step;
+  if (!(t < r.tmax)) {
+    out[0] = out[1] = out[2] = O.bg;  // light = 1
+    return;
+  }
+  Marcher<G> m;
+  m.init();
+  float delta_t;
+  long long idx = m.locate(T, r, O.step, t, l, mask, delta_t);
+  for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
     const float* __restrict__ val = T.data + idx * D;
     const float sigma = __ldg(val + D - 1);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (l < K) {
+      c0 = __ldg(val + l);
+      c1 = __ldg(val + K + l);
+      c2 = __ldg(val + 2 * K + l);
+    }
+    const float t_next = t + delta_t;
+    const bool more = t_next < r.tmax;
+    float delta_n = 0.f;
+    long long idx_n = 0;
+    if (more) idx_n = m.locate(T, r, O.step, t_next, l, mask, delta_n);
     ++visits;
     if (sigma > O.sigma_thresh) {
       ++hits;
       const float att = expf(-delta_t * r.delta_scale * sigma);
       const float weight = light * (1.0f - att);
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      if (l < K) {
-        p0 = basis_l * __ldg(val + l);
-        p1 = basis_l * __ldg(val + K + l);
-        p2 = basis_l * __ldg(val + 2 * K + l);
-      }
-      p0 = group_sum<G>(p0, mask);
-      p1 = group_sum<G>(p1, mask);
-      p2 = group_sum<G>(p2, mask);
+      const float p0 = group_sum<G>(basis_l * c0, mask);
+      const float p1 = group_sum<G>(basis_l * c1, mask);
+      const float p2 = group_sum<G>(basis_l * c2, mask);
       out[0] += weight * sigmoidf(p0);
       out[1] += weight * sigmoidf(p1);
       out[2] += weight * sigmoidf(p2);
@@ -200,7 +307,10 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
         return;
       }
     }
-    t += delta_t;
+    if (!more) break;
+    t = t_next;
+    idx = idx_n;
+    delta_t = delta_n;
   }
   out[0] += light * O.bg;
   out[1] += light * O.bg;
@@ -218,30 +328,31 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
   float light = 1.0f;
   float t = r.tmin;
   const int K = T.K, D = T.D;
-  const int gl = l % G;
-  for (int it = 0; t < r.tmax && it < MAX_MARCH_STEPS; ++it) {
-    float pos[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) pos[a] = r.o[a] + t * r.d[a];
-    float cube;
-    const long long idx = query_leaf(T.child, T.N, pos, cube);
-    float smin, smax;
-    dda_unit(pos, r.invd, smin, smax);
-    const float delta_t = (smax - smin) / cube + O.step;
+  if (!(t < r.tmax)) return;
+  Marcher<G> m;
+  m.init();
+  float delta_t;
+  long long idx = m.locate(T, r, O.step, t, l, mask, delta_t);
+  for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
     const float* __restrict__ val = T.data + idx * D;
     const float sigma = __ldg(val + D - 1);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (l < K) {
+      c0 = __ldg(val + l);
+      c1 = __ldg(val + K + l);
+      c2 = __ldg(val + 2 * K + l);
+    }
+    const float t_next = t + delta_t;
+    const bool more = t_next < r.tmax;
+    float delta_n = 0.f;
+    long long idx_n = 0;
+    if (more) idx_n = m.locate(T, r, O.step, t_next, l, mask, delta_n);
     if (sigma > 0.0f) {
       const float att = expf(-delta_t * r.delta_scale * sigma);
       const float weight = light * (1.0f - att);
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      if (l < K) {
-        p0 = basis_l * __ldg(val + l);
-        p1 = basis_l * __ldg(val + K + l);
-        p2 = basis_l * __ldg(val + 2 * K + l);
-      }
-      p0 = group_sum<G>(p0, mask);
-      p1 = group_sum<G>(p1, mask);
-      p2 = group_sum<G>(p2, mask);
+      const float p0 = group_sum<G>(basis_l * c0, mask);
+      const float p1 = group_sum<G>(basis_l * c1, mask);
+      const float p2 = group_sum<G>(basis_l * c2, mask);
       const float s0 = sigmoidf(p0), s1 = sigmoidf(p1), s2 = sigmoidf(p2);
       float* gv = grad + idx * D;
       if (l < K) {
@@ -252,9 +363,12 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
       const float total = s0 * g[0] + s1 * g[1] + s2 * g[2];
       light *= att;
       accum -= weight * total;
-      if (gl == 0) atomicAdd(gv + D - 1, delta_t * r.delta_scale * (total * light - accum));
+      if (l == 0) atomicAdd(gv + D - 1, delta_t * r.delta_scale * (total * light - accum));
     }
-    t += delta_t;
+    if (!more) break;
+    t = t_next;
+    idx = idx_n;
+    delta_t = delta_n;
   }
 }
 

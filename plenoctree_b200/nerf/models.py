@@ -183,9 +183,10 @@ def ctypes_ref(struct):
     return ctypes.addressof(struct)
 
 
-def get_model_state(args, device="cuda", seed=20200823):
-    """models.get_model_state (nerf_sh/nerf/models.py:38-49) without the checkpoint restore: builds the
-    model from a flags-like object and initialises parameters + Adam moments."""
+def get_model_state(args, device="cuda", seed=20200823, restore=True):
+    """models.get_model_state (nerf_sh/nerf/models.py:38-49): builds the model from a flags-like object,
+    initialises parameters + Adam moments and, when `restore` and args.train_dir holds a flax-format
+    `checkpoint_<step>`, restores parameters / moments / step from the newest one (checkpoints.py)."""
     from .train import TrainState
     model = NerfModel(sh_deg=args.sh_deg, num_coarse_samples=args.num_coarse_samples,
                       num_fine_samples=args.num_fine_samples, near=args.near, far=args.far,
@@ -193,4 +194,8 @@ def get_model_state(args, device="cuda", seed=20200823):
                       max_rays=getattr(args, "batch_size", 4096),
                       sparsity_npoints=getattr(args, "sparsity_npoints", 0), device=device)
     model.init_params(seed)
-    return model, TrainState(model)
+    state = TrainState(model)
+    if restore and getattr(args, "train_dir", None):
+        from . import checkpoints
+        checkpoints.restore_checkpoint(args.train_dir, model, state)
+    return model, state
