@@ -128,6 +128,11 @@ typedef struct pob_render_config {
   int white_bkgd;           /* flag white_bkgd */
   int max_rays;             /* capacity of the workspace in rays per call */
   int sparsity_npoints;     /* flag sparsity_npoints (training workspace only) */
+  /* model_utils.add_gaussian_noise (nerf_sh/nerf/model_utils.py:317-332; flag noise_std, utils.py:137-142):
+   * optional per-sample normal draws ALREADY multiplied by noise_std, added to raw sigma before relu at the
+   * coarse [n_rays, Nc] and fine [n_rays, Nc+Nf] level; NULL = off (randomized False or noise_std None). */
+  const float* sigma_noise_coarse_dev;
+  const float* sigma_noise_fine_dev;
 } pob_render_config;
 
 /* bytes of device scratch the render (training=0) / training (training=1) calls need */

@@ -58,7 +58,8 @@ SIGNATURES = {
 
 class RenderConfig(_c.Structure):
     _fields_ = [("sh_deg", _i), ("num_coarse_samples", _i), ("num_fine_samples", _i), ("white_bkgd", _i),
-                ("max_rays", _i), ("sparsity_npoints", _i)]
+                ("max_rays", _i), ("sparsity_npoints", _i), ("sigma_noise_coarse_dev", _vp),
+                ("sigma_noise_fine_dev", _vp)]
 
 
 class TrainHParams(_c.Structure):

@@ -453,6 +453,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             o.x = 1.f / (1.f + expf(-pre[0]));
             o.y = 1.f / (1.f + expf(-pre[1]));
             o.z = 1.f / (1.f + expf(-pre[2]));
+            if (p.sigma_noise != nullptr) sigma_raw += __ldg(p.sigma_noise + s);  // add_gaussian_noise
             o.w = fmaxf(sigma_raw, 0.f);
             p.out_rgbs[s] = o;
           }

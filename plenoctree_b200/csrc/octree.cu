@@ -15,6 +15,7 @@
 // finish with log2(G) shuffles, and the backward scatter issues coalesced RED.ADD.F32 (one L2 atomic
 // sector per 8 lanes).  Pixels are tiled 4x4 (4x2) per CTA so neighbouring rays share L1 lines.
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/plenoctree_b200.h"
 #include "capi_util.h"
@@ -254,8 +255,8 @@ struct Marcher {
 // ---- forward march of one ray by one lane group -------------------------------------------------------
 // Software-pipelined: the loads of the current leaf (sigma and this lane's three coefficients, issued
 // unconditionally) are in flight while the next leaf is located; the march itself never depends on the data.
-template <int G>
-__device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, const Ray& r, float basis_l, int l,
+template <int G, int KPL>
+__device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, const Ray& r, const float* basis_l, int l,
                                               unsigned mask, float* out, unsigned& visits, unsigned& hits) {
   if (!r.hit) {
     out[0] = out[1] = out[2] = O.bg;
@@ -276,11 +277,16 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
   for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
     const float* __restrict__ val = T.data + idx * D;
     const float sigma = __ldg(val + D - 1);
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (l < K) {
-      c0 = __ldg(val + l);
-      c1 = __ldg(val + K + l);
-      c2 = __ldg(val + 2 * K + l);
+    float c0[KPL], c1[KPL], c2[KPL];  // lane l owns basis functions l, l+G, ...
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int k = l + j * G;
+      c0[j] = c1[j] = c2[j] = 0.f;
+      if (k < K) {
+        c0[j] = __ldg(val + k);
+        c1[j] = __ldg(val + K + k);
+        c2[j] = __ldg(val + 2 * K + k);
+      }
     }
     const float t_next = t + delta_t;
     const bool more = t_next < r.tmax;
@@ -292,9 +298,16 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
       ++hits;
       const float att = expf(-delta_t * r.delta_scale * sigma);
       const float weight = light * (1.0f - att);
-      const float p0 = group_sum<G>(basis_l * c0, mask);
-      const float p1 = group_sum<G>(basis_l * c1, mask);
-      const float p2 = group_sum<G>(basis_l * c2, mask);
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        p0 += basis_l[j] * c0[j];
+        p1 += basis_l[j] * c1[j];
+        p2 += basis_l[j] * c2[j];
+      }
+      p0 = group_sum<G>(p0, mask);
+      p1 = group_sum<G>(p1, mask);
+      p2 = group_sum<G>(p2, mask);
       out[0] += weight * sigmoidf(p0);
       out[1] += weight * sigmoidf(p1);
       out[2] += weight * sigmoidf(p2);
@@ -320,8 +333,8 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
 // ---- backward march: colour and density gradients in one pass ---------------------------------------
 // accum enters as sum_j w_j (c_j . g) + T_end * bg * sum(g) = g . out (svox computes it with an extra march:
 // trace_ray_backward pass 1); every contributing leaf then peels its own term off.
-template <int G>
-__device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, const Ray& r, float basis_l, int l,
+template <int G, int KPL>
+__device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, const Ray& r, const float* basis_l, int l,
                                                unsigned mask, const float* g, float accum,
                                                float* __restrict__ grad) {
   if (!r.hit) return;
@@ -336,11 +349,16 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
   for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
     const float* __restrict__ val = T.data + idx * D;
     const float sigma = __ldg(val + D - 1);
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (l < K) {
-      c0 = __ldg(val + l);
-      c1 = __ldg(val + K + l);
-      c2 = __ldg(val + 2 * K + l);
+    float c0[KPL], c1[KPL], c2[KPL];  // lane l owns basis functions l, l+G, ...
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int k = l + j * G;
+      c0[j] = c1[j] = c2[j] = 0.f;
+      if (k < K) {
+        c0[j] = __ldg(val + k);
+        c1[j] = __ldg(val + K + k);
+        c2[j] = __ldg(val + 2 * K + k);
+      }
     }
     const float t_next = t + delta_t;
     const bool more = t_next < r.tmax;
@@ -350,15 +368,29 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
     if (sigma > 0.0f) {
       const float att = expf(-delta_t * r.delta_scale * sigma);
       const float weight = light * (1.0f - att);
-      const float p0 = group_sum<G>(basis_l * c0, mask);
-      const float p1 = group_sum<G>(basis_l * c1, mask);
-      const float p2 = group_sum<G>(basis_l * c2, mask);
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        p0 += basis_l[j] * c0[j];
+        p1 += basis_l[j] * c1[j];
+        p2 += basis_l[j] * c2[j];
+      }
+      p0 = group_sum<G>(p0, mask);
+      p1 = group_sum<G>(p1, mask);
+      p2 = group_sum<G>(p2, mask);
       const float s0 = sigmoidf(p0), s1 = sigmoidf(p1), s2 = sigmoidf(p2);
       float* gv = grad + idx * D;
-      if (l < K) {
-        atomicAdd(gv + l, basis_l * (weight * s0 * (1.0f - s0) * g[0]));
-        atomicAdd(gv + K + l, basis_l * (weight * s1 * (1.0f - s1) * g[1]));
-        atomicAdd(gv + 2 * K + l, basis_l * (weight * s2 * (1.0f - s2) * g[2]));
+      const float t0 = weight * s0 * (1.0f - s0) * g[0];
+      const float t1 = weight * s1 * (1.0f - s1) * g[1];
+      const float t2 = weight * s2 * (1.0f - s2) * g[2];
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = l + j * G;
+        if (k < K) {
+          atomicAdd(gv + k, basis_l[j] * t0);
+          atomicAdd(gv + K + k, basis_l[j] * t1);
+          atomicAdd(gv + 2 * K + k, basis_l[j] * t2);
+        }
       }
       const float total = s0 * g[0] + s1 * g[1] + s2 * g[2];
       light *= att;
@@ -404,20 +436,28 @@ __device__ __forceinline__ bool fetch_ray(const RaySrc& S, const TreeDev& T, Ray
   return true;
 }
 
-template <int G>
-__device__ __forceinline__ float lane_basis(const TreeDev& T, const Ray& r, int l) {
-  if (T.rgba) return 1.0f;
+template <int G, int KPL>
+__device__ __forceinline__ void lane_basis(const TreeDev& T, const Ray& r, int l, float* bl) {
+  if (T.rgba) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) bl[j] = 1.0f;
+    return;
+  }
   float b[25];
   const int deg = T.K >= 25 ? 4 : T.K >= 16 ? 3 : T.K >= 9 ? 2 : T.K >= 4 ? 1 : 0;
   sh_basis(deg, r.vdir[0], r.vdir[1], r.vdir[2], b);
-  float v = 0.f;
 #pragma unroll
-  for (int k = 0; k < 25; ++k)
-    if (k == l) v = b[k];
-  return l < T.K ? v : 0.f;
+  for (int j = 0; j < KPL; ++j) {
+    const int want = l + j * G;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k)
+      if (k == want && k < T.K) v = b[k];
+    bl[j] = v;
+  }
 }
 
-template <int G>
+template <int G, int KPL>
 __global__ void __launch_bounds__(256) octree_render_kernel(TreeDev T, Opts O, RaySrc S, float* __restrict__ out_rgb,
                                                             unsigned long long* __restrict__ counters) {
   Ray r;
@@ -425,10 +465,11 @@ __global__ void __launch_bounds__(256) octree_render_kernel(TreeDev T, Opts O, R
   if (!fetch_ray<G>(S, T, r, oi)) return;
   const int l = threadIdx.x % G;
   const unsigned mask = group_mask<G>();
-  const float bl = lane_basis<G>(T, r, l);
+  float bl[KPL];
+  lane_basis<G, KPL>(T, r, l, bl);
   float out[3];
   unsigned visits = 0, hits = 0;
-  trace_forward<G>(T, O, r, bl, l, mask, out, visits, hits);
+  trace_forward<G, KPL>(T, O, r, bl, l, mask, out, visits, hits);
   if (l < 3) out_rgb[3 * oi + l] = l == 0 ? out[0] : l == 1 ? out[1] : out[2];
   if (counters != nullptr && l == 0) {
     atomicAdd(counters + 0, (unsigned long long)visits);
@@ -437,7 +478,7 @@ __global__ void __launch_bounds__(256) octree_render_kernel(TreeDev T, Opts O, R
 }
 
 // VolumeRenderer backward for an upstream gradient d loss / d rgb  (svox trace_ray_backward)
-template <int G>
+template <int G, int KPL>
 __global__ void __launch_bounds__(256) octree_backward_kernel(TreeDev T, Opts O, RaySrc S,
                                                               const float* __restrict__ grad_out,
                                                               float* __restrict__ grad_data) {
@@ -446,22 +487,23 @@ __global__ void __launch_bounds__(256) octree_backward_kernel(TreeDev T, Opts O,
   if (!fetch_ray<G>(S, T, r, oi)) return;
   const int l = threadIdx.x % G;
   const unsigned mask = group_mask<G>();
-  const float bl = lane_basis<G>(T, r, l);
+  float bl[KPL];
+  lane_basis<G, KPL>(T, r, l, bl);
   float out[3];
   unsigned visits = 0, hits = 0;
   Opts Of = O;
   Of.sigma_thresh = 0.f;
   Of.stop_thresh = 0.f;
-  trace_forward<G>(T, Of, r, bl, l, mask, out, visits, hits);
+  trace_forward<G, KPL>(T, Of, r, bl, l, mask, out, visits, hits);
   float g[3] = {__ldg(grad_out + 3 * oi), __ldg(grad_out + 3 * oi + 1), __ldg(grad_out + 3 * oi + 2)};
   const float accum = g[0] * out[0] + g[1] * out[1] + g[2] * out[2];
-  trace_backward<G>(T, Of, r, bl, l, mask, g, accum, grad_data);
+  trace_backward<G, KPL>(T, Of, r, bl, l, mask, g, accum, grad_data);
 }
 
 // One training pass over a camera slab (octree/optimization.py:201-207 minus the optimiser):
 //   im = render_persp(c2w); mse = mean((clamp(im,0,1) - gt)^2); mse.backward()
 // g = grad_scale * 2 * (clamp(im) - gt) inside the clamp range, 0 outside (torch.clamp's gradient).
-template <int G>
+template <int G, int KPL>
 __global__ void __launch_bounds__(256) octree_train_kernel(TreeDev T, Opts O, RaySrc S, const float* __restrict__ gt,
                                                            float grad_scale, float* __restrict__ grad_data,
                                                            double* __restrict__ sq_err_sum,
@@ -473,10 +515,11 @@ __global__ void __launch_bounds__(256) octree_train_kernel(TreeDev T, Opts O, Ra
   if (have) {
     const int l = threadIdx.x % G;
     const unsigned mask = group_mask<G>();
-    const float bl = lane_basis<G>(T, r, l);
+    float bl[KPL];
+    lane_basis<G, KPL>(T, r, l, bl);
     float out[3];
     unsigned visits = 0, hits = 0;
-    trace_forward<G>(T, O, r, bl, l, mask, out, visits, hits);
+    trace_forward<G, KPL>(T, O, r, bl, l, mask, out, visits, hits);
     float g[3];
     float accum = 0.f;
 #pragma unroll
@@ -488,7 +531,7 @@ __global__ void __launch_bounds__(256) octree_train_kernel(TreeDev T, Opts O, Ra
       accum += g[c] * out[c];
     }
     if (out_rgb != nullptr && l < 3) out_rgb[3 * oi + l] = l == 0 ? out[0] : l == 1 ? out[1] : out[2];
-    if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) trace_backward<G>(T, O, r, bl, l, mask, g, accum, grad_data);
+    if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) trace_backward<G, KPL>(T, O, r, bl, l, mask, g, accum, grad_data);
     if (l != 0) err = 0.f;
   }
   // CTA reduction of the squared error (one double atomic per CTA)
@@ -642,6 +685,29 @@ int opts_dev(const char* where, const pob_octree_opts* o, Opts& O) {
   return 0;
 }
 
+// Group width / coefficients per lane.  Default: 8 lanes per ray (twice the rays in flight of 16 lanes at the same
+// occupancy; the march is latency bound), lane l owns basis functions l, l+8, ...  POB_OCTREE_G=16|32 selects the
+// one-coefficient-per-lane mappings (profiling).
+int group_width(int K) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("POB_OCTREE_G");
+    env = e ? atoi(e) : 0;
+  }
+  if (env == 32) return 32;
+  if (env == 16) return K > 16 ? 32 : 16;
+  return 8;
+}
+
+#define POB_OCTREE_DISPATCH(KERNEL, G, K, ...)                                   \
+  do {                                                                           \
+    if ((G) == 32) KERNEL<32, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);           \
+    else if ((G) == 16) KERNEL<16, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);      \
+    else if ((K) <= 8) KERNEL<8, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);        \
+    else if ((K) <= 16) KERNEL<8, 2><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
+    else KERNEL<8, 4><<<blocks, 256, 0, st>>>(__VA_ARGS__);                      \
+  } while (0)
+
 int ray_src(const char* where, const float* o, const float* d, const float* v, long long n, const pob_camera* cam,
             int row0, int nrows, RaySrc& S, unsigned& blocks, int G) {
   const int rpb = 256 / G;
@@ -688,16 +754,13 @@ int pob_octree_render(const pob_octree* tree, const pob_octree_opts* opts, const
   unsigned blocks = 0;
   if (int rc = tree_dev(W, tree, T)) return rc;
   if (int rc = opts_dev(W, opts, O)) return rc;
-  const int G = T.K > 16 ? 32 : 16;
+  const int G = group_width(T.K);
   if (int rc = ray_src(W, origins_dev, dirs_dev, vdirs_dev, n_rays, cam, row0, nrows, S, blocks, G)) return rc;
   if (!out_rgb_dev) return pob_fail(W, "output pointer is NULL");
   if (blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   pob_count_launch();
-  if (G == 32)
-    octree_render_kernel<32><<<blocks, 256, 0, st>>>(T, O, S, out_rgb_dev, counters_dev);
-  else
-    octree_render_kernel<16><<<blocks, 256, 0, st>>>(T, O, S, out_rgb_dev, counters_dev);
+  POB_OCTREE_DISPATCH(octree_render_kernel, G, T.K, T, O, S, out_rgb_dev, counters_dev);
   POB_CUDA(W, cudaGetLastError());
   return 0;
 }
@@ -712,16 +775,13 @@ int pob_octree_render_backward(const pob_octree* tree, const pob_octree_opts* op
   unsigned blocks = 0;
   if (int rc = tree_dev(W, tree, T)) return rc;
   if (int rc = opts_dev(W, opts, O)) return rc;
-  const int G = T.K > 16 ? 32 : 16;
+  const int G = group_width(T.K);
   if (int rc = ray_src(W, origins_dev, dirs_dev, vdirs_dev, n_rays, cam, row0, nrows, S, blocks, G)) return rc;
   if (!grad_out_dev || !grad_data_dev) return pob_fail(W, "gradient pointer is NULL");
   if (blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   pob_count_launch();
-  if (G == 32)
-    octree_backward_kernel<32><<<blocks, 256, 0, st>>>(T, O, S, grad_out_dev, grad_data_dev);
-  else
-    octree_backward_kernel<16><<<blocks, 256, 0, st>>>(T, O, S, grad_out_dev, grad_data_dev);
+  POB_OCTREE_DISPATCH(octree_backward_kernel, G, T.K, T, O, S, grad_out_dev, grad_data_dev);
   POB_CUDA(W, cudaGetLastError());
   return 0;
 }
@@ -739,18 +799,14 @@ int pob_octree_train_persp(const pob_octree* tree, const pob_octree_opts* opts, 
   if (!cam) return pob_fail(W, "camera is NULL");
   if (O.sigma_thresh != 0.f || O.stop_thresh != 0.f)
     return pob_fail(W, "training renders with sigma_thresh = stop_thresh = 0 (svox fast=False)");
-  const int G = T.K > 16 ? 32 : 16;
+  const int G = group_width(T.K);
   if (int rc = ray_src(W, nullptr, nullptr, nullptr, 0, cam, row0, nrows, S, blocks, G)) return rc;
   if (!gt_rgb_dev || !grad_data_dev) return pob_fail(W, "gt / gradient pointer is NULL");
   if (blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   pob_count_launch();
-  if (G == 32)
-    octree_train_kernel<32><<<blocks, 256, 0, st>>>(T, O, S, gt_rgb_dev, grad_scale, grad_data_dev, sq_err_sum_dev,
-                                                    out_rgb_dev);
-  else
-    octree_train_kernel<16><<<blocks, 256, 0, st>>>(T, O, S, gt_rgb_dev, grad_scale, grad_data_dev, sq_err_sum_dev,
-                                                    out_rgb_dev);
+  POB_OCTREE_DISPATCH(octree_train_kernel, G, T.K, T, O, S, gt_rgb_dev, grad_scale, grad_data_dev, sq_err_sum_dev,
+                      out_rgb_dev);
   POB_CUDA(W, cudaGetLastError());
   return 0;
 }

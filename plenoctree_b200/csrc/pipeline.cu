@@ -156,6 +156,7 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
   { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sample_coarse(z_base, t_rand, R, Nc, C.z, st)); }
   {
     FwdParams p = ray_fwd_params(pk_c, c.sh_deg, o, d, v, C.z, R, Nc, C.rgbs);
+    p.sigma_noise = c.sigma_noise_coarse_dev;
     if (save) {
       p.save_h = C.H;
       p.save_e = C.E;
@@ -172,6 +173,7 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
     else
       { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sample_pdf(C.z, C.weights, u, u_per_ray, R, Nc, Nf, F.z, st)); }
     FwdParams p = ray_fwd_params(pk_f, c.sh_deg, o, d, v, F.z, R, Nc + Nf, F.rgbs);
+    p.sigma_noise = c.sigma_noise_fine_dev;
     if (save) {
       p.save_h = F.H;
       p.save_e = F.E;

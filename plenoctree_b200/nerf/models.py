@@ -54,7 +54,7 @@ class NerfModel:
 
     def __init__(self, sh_deg=3, num_coarse_samples=64, num_fine_samples=128, near=2.0, far=6.0,
                  white_bkgd=True, lindisp=False, max_rays=4096, sparsity_npoints=0, device="cuda",
-                 precision=PREC_FP16):
+                 precision=PREC_FP16, noise_std=None):
         if not (-1 <= sh_deg <= 4):
             raise ValueError("sh_deg must be in [-1, 4]")
         self.sh_deg = sh_deg
@@ -66,6 +66,7 @@ class NerfModel:
         self.max_rays = int(max_rays)
         self.sparsity_npoints = int(sparsity_npoints)
         self.precision = precision
+        self.noise_std = noise_std   # flag noise_std (nerf_sh/nerf/utils.py:137-142); None = no density noise
         self.device = torch.device(device)
         self.num_mlps = 2 if self.num_fine_samples > 0 else 1
         self.P = int(lib.pob_param_count(sh_deg))
@@ -120,7 +121,28 @@ class NerfModel:
         return self.blobs[0] if (coarse or self.num_mlps == 1) else self.blobs[1]
 
     # ---- NerfModel.__call__ ------------------------------------------------------------------
-    def __call__(self, rays, randomized=False, t_rand=None, u=None, precision=None, z_fine=None):
+    def _set_sigma_noise(self, n, randomized, sigma_noise):
+        """add_gaussian_noise (nerf_sh/nerf/model_utils.py:317-332): when randomized and noise_std is set, raw sigma
+        of both levels gets normal(0, noise_std^2) noise.  sigma_noise = (coarse [n,Nc], fine [n,Nc+Nf]) passes the
+        already scaled draws explicitly (parity tests).  Returns the tensors (kept alive by the caller)."""
+        nc = nf = None
+        if sigma_noise is not None:
+            nc = _cuda_f32(sigma_noise[0], "sigma_noise[0]", self.num_coarse_samples)
+            if self.num_mlps == 2:
+                nf = _cuda_f32(sigma_noise[1], "sigma_noise[1]", self.num_coarse_samples + self.num_fine_samples)
+        elif randomized and self.noise_std is not None and self.noise_std > 0:
+            nc = torch.randn((n, self.num_coarse_samples), device=self.device) * float(self.noise_std)
+            if self.num_mlps == 2:
+                nf = torch.randn((n, self.num_coarse_samples + self.num_fine_samples),
+                                 device=self.device) * float(self.noise_std)
+        for t in (nc, nf):
+            if t is not None and t.shape[0] != n:
+                raise ValueError("sigma_noise must have one row per ray")
+        self.cfg.sigma_noise_coarse_dev = ptr(nc)
+        self.cfg.sigma_noise_fine_dev = ptr(nf)
+        return nc, nf
+
+    def __call__(self, rays, randomized=False, t_rand=None, u=None, precision=None, z_fine=None, sigma_noise=None):
         """-> [(rgb_coarse, disp_coarse, acc_coarse), (rgb, disp, acc)] for up to max_rays rays.
 
         randomized=True draws the stratified jitter / inverse-CDF uniforms on the device unless
@@ -133,6 +155,7 @@ class NerfModel:
             raise ValueError(f"{n} rays exceed max_rays={self.max_rays}; chunk the call (utils.render_image)")
         t_rand, u, upr = self._uniforms(n, randomized, t_rand, u)
         z_fine = None if z_fine is None else _cuda_f32(z_fine, "z_fine")   # keep alive until the launch
+        noise = self._set_sigma_noise(n, randomized, sigma_noise)           # noqa: F841  (same)
         ws = self.workspace(False)
         out_c = torch.empty((n, 5), dtype=torch.float32, device=self.device)
         out_f = torch.empty((n, 5), dtype=torch.float32, device=self.device) if self.num_mlps == 2 else None

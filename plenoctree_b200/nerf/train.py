@@ -59,7 +59,8 @@ def default_loss_scale(n_rays):
 
 
 def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
-                  randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None, z_fine=None):
+                  randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None, z_fine=None,
+                  sigma_noise=None):
     """value_and_grad(loss_fn) for this rank's shard; fills state.grads / state.stats_raw (device)."""
     rays = batch["rays"]
     o = _cuda_f32(rays.origins, "rays.origins", 3)
@@ -77,6 +78,7 @@ def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.0
         if sp_points.shape[0] != model.sparsity_npoints:
             raise ValueError("sp_points must have sparsity_npoints rows")
     z_fine = None if z_fine is None else _cuda_f32(z_fine, "z_fine")   # keep alive until the launch
+    noise = model._set_sigma_noise(n, randomized, sigma_noise)          # noqa: F841  (same)
     ws = model.workspace(True)
     hp = TrainHParams(float(sparsity_weight if use_sp else 0.0), float(sparsity_length),
                       float(loss_scale or default_loss_scale(n)))

@@ -255,3 +255,49 @@ def test_full_frame_psnr_parity():
                                              psnr_gpu_vs_ref=float(psnr_vs_ref)))
         assert abs(psnr_gpu - psnr_ref) < 0.05, (pname, psnr_gpu, psnr_ref)
         assert psnr_vs_ref > 55.0
+
+
+def test_sigma_noise_forward_vs_oracle():
+    """add_gaussian_noise on raw sigma (model_utils.py:317-332) at both levels, explicit draws."""
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200 import ops
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    sh_deg, R, nf = 3, 256, 128
+    fc = O.init_flat_params(sh_deg, 31, bias_scale=0.05)
+    ff = O.init_flat_params(sh_deg, 32, bias_scale=0.05)
+    for f in (fc, ff):
+        off = O.param_count(sh_deg) - 48 - 1 - 256 * 48 - 256
+        f[off:off + 256] *= 30.0
+    o, d, v = _rays(R, 5)
+    rs = np.random.RandomState(10)
+    t_rand = rs.uniform(0, 1, size=(R, 64)).astype(np.float32)
+    u = rs.uniform(0, 1, size=(R, nf)).astype(np.float32)
+    noise = (rs.normal(size=(R, 64)).astype(np.float32) * 2.0, rs.normal(size=(R, 64 + nf)).astype(np.float32) * 2.0)
+    rays_t = tuple(torch.from_numpy(a) for a in (o, d, v))
+    with torch.no_grad():
+        ref, aux = O.nerf_forward(O.unflatten(fc, sh_deg), O.unflatten(ff, sh_deg), sh_deg, rays_t, 64, nf, 2.0, 6.0,
+                                  True, torch.from_numpy(t_rand), torch.from_numpy(u), return_aux=True,
+                                  sigma_noise=tuple(torch.from_numpy(a) for a in noise))
+        plain = O.nerf_forward(O.unflatten(fc, sh_deg), O.unflatten(ff, sh_deg), sh_deg, rays_t, 64, nf, 2.0, 6.0,
+                               True, torch.from_numpy(t_rand), torch.from_numpy(u))
+    assert float((ref[1][0] - plain[1][0]).abs().max()) > 1e-2   # the noise matters at this scale
+    model = NerfModel(sh_deg=sh_deg, num_coarse_samples=64, num_fine_samples=nf, max_rays=R)
+    model.set_params(np.concatenate([fc, ff]))
+    got = model(Rays(o, d, v), randomized=True, t_rand=t_rand, u=u, precision=ops.PREC_FP16X3,
+                z_fine=aux["z_fine"].numpy(), sigma_noise=noise)
+    torch.cuda.synchronize()
+    for lvl in range(2):
+        e = float((got[lvl][0].cpu() - ref[lvl][0]).abs().max())
+        _record(f"sigma_noise_lvl{lvl}", dict(rgb_max_abs=e))
+        assert e < 1e-4, (lvl, e)
+    # noise_std flag: drawn on the device when randomized, identity otherwise
+    model.noise_std = 1.0
+    a = model(Rays(o, d, v), randomized=False)[1][0].cpu()
+    model.noise_std = None
+    b = model(Rays(o, d, v), randomized=False)[1][0].cpu()
+    assert float((a - b).abs().max()) == 0.0
+    model.noise_std = 1.0
+    c = model(Rays(o, d, v), randomized=True, t_rand=t_rand, u=u)[1][0].cpu()
+    model.noise_std = None
+    e = model(Rays(o, d, v), randomized=True, t_rand=t_rand, u=u)[1][0].cpu()
+    assert float((c - e).abs().max()) > 1e-3

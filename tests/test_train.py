@@ -198,3 +198,32 @@ np.save(sys.argv[1], state.grads.cpu().numpy())
     # identical operands, same fp32 MMA accumulation per tile; only the order in which tiles are summed
     # into a consumer's accumulator differs
     assert float(np.linalg.norm(a - b) / np.linalg.norm(a)) < 1e-4
+
+
+def test_loss_and_grad_with_sigma_noise():
+    """row a4 in training: the relu mask of sigma follows the NOISED pre-activation (train.py:70 -> models.py:274)."""
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf import train as T
+    sh_deg, R, nf = 3, 64, 128
+    fc, ff, rays, px, t_rand, u, _ = _setup(sh_deg, R, nf, 0, 99)
+    rs = np.random.RandomState(3)
+    noise = (rs.normal(size=(R, 64)).astype(np.float32) * 0.5, rs.normal(size=(R, 64 + nf)).astype(np.float32) * 0.5)
+    cfg = dict(num_coarse_samples=64, num_fine_samples=nf, near=2.0, far=6.0, white_bkgd=True, sparsity_weight=0.0,
+               sparsity_length=0.05)
+    stats_o, gc_o, gf_o = O.loss_and_grads(fc, ff, sh_deg, rays, px, cfg, t_rand, u, None, sigma_noise=noise)
+    _, gc_p, gf_p = O.loss_and_grads(fc, ff, sh_deg, rays, px, cfg, t_rand, u, None)
+    ref = np.concatenate([gc_o, gf_o])
+    plain = np.concatenate([gc_p, gf_p])
+    assert np.linalg.norm(ref - plain) / np.linalg.norm(plain) > 0.05   # noise changes the gradient visibly
+    model = NerfModel(sh_deg=sh_deg, num_coarse_samples=64, num_fine_samples=nf, max_rays=R)
+    model.set_params(np.concatenate([fc, ff]))
+    state = T.TrainState(model)
+    T.loss_and_grad(model, state, {"rays": Rays(*rays), "pixels": px}, sparsity_weight=0.0, randomized=True,
+                    t_rand=t_rand, u=u, z_fine=stats_o["_z_fine"], sigma_noise=noise)
+    torch.cuda.synchronize()
+    g = state.grads.cpu().numpy()
+    tot = float(np.linalg.norm(g - ref) / np.linalg.norm(ref))
+    cos = float(np.dot(g, ref) / (np.linalg.norm(g) * np.linalg.norm(ref)))
+    _record("sigma_noise_grad", dict(rel_l2=tot, cosine=cos))
+    assert tot < 2e-2 and cos > 0.9995, (tot, cos)
