@@ -50,3 +50,64 @@ def test_single_process_is_identity():
     with pytest.raises(ValueError):
         shard_batch(1000, 0, 3)
     assert [grid_slab(10, r, 3) for r in range(3)] == [(0, 4), (4, 3), (7, 3)]
+
+
+def test_octree_row_slabs_cover_image():
+    from plenoctree_b200.octree.optimization import row_slab
+    for H, world in ((800, 8), (37, 4), (5, 8), (1080, 3)):
+        slabs = [row_slab(H, r, world) for r in range(world)]
+        assert slabs[0][0] == 0 and sum(n for _, n in slabs) == H
+        for (a, n), (b, _) in zip(slabs, slabs[1:]):
+            assert a + n == b
+
+
+def _octree_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    # both ranks share cuda:0 (one-GPU box), so the collective is gloo on device tensors; on a multi-GPU box the
+    # same code runs one rank per GPU over NCCL (scripts/bench_octree_dist.py)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from tests.test_octree import look_at_pose, make_tree, to_device_tree
+        from plenoctree_b200.octree import VolumeRenderer, optimization as OPT
+        torch.cuda.set_device(0)
+        otree = make_tree(61, 3, "SH16")
+        tree = to_device_tree(otree)
+        W, H, fx = 40, 33, 50.0
+        poses = [look_at_pose(s) for s in range(3)]
+        gts = [torch.from_numpy(np.random.RandomState(s).uniform(0, 1, size=(H, W, 3)).astype(np.float32)) for s in range(3)]
+        r = VolumeRenderer(tree, step_size=1e-3)
+        psnr = OPT.train_epoch(tree, r, poses, gts, H, W, fx, 2e3)
+        q.put((rank, float(psnr), tree.data[:otree.n_internal].cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_octree_epoch_two_ranks_equals_one_rank():
+    """C5 ray-parallel: pixel-row slabs per rank + one all-reduce of the dense gradient per image must
+    reproduce the single-process epoch (same SGD sequence) up to fp32 summation order."""
+    import numpy as np
+    from tests.test_octree import look_at_pose, make_tree, to_device_tree
+    from plenoctree_b200.octree import VolumeRenderer, optimization as OPT
+    otree = make_tree(61, 3, "SH16")
+    tree = to_device_tree(otree)
+    W, H, fx = 40, 33, 50.0
+    poses = [look_at_pose(s) for s in range(3)]
+    gts = [torch.from_numpy(np.random.RandomState(s).uniform(0, 1, size=(H, W, 3)).astype(np.float32)) for s in range(3)]
+    psnr1 = OPT.train_epoch(tree, VolumeRenderer(tree, step_size=1e-3), poses, gts, H, W, fx, 2e3)
+    want = tree.data[:otree.n_internal].cpu().numpy()
+    assert np.abs(want - otree.data[:otree.n_internal]).max() > 1e-3   # the epoch changed the tree
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_octree_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, psnr2, data in res:
+        assert abs(psnr2 - psnr1) < 1e-3, (rank, psnr1, psnr2)
+        assert np.abs(data - want).max() <= 1e-4 * np.abs(want).max(), rank
