@@ -247,30 +247,52 @@ def main():
         T.train_step(model, state, batch_from(pool, i), lr_of(state.step), sparsity_length=sp_len,
                      sparsity_radius=sp_rad)
 
-    stage = torch.empty((RAYS, 12), dtype=torch.float32, device=dev)
-    stats_host = torch.empty(8, dtype=torch.float32).pin_memory()
+    # end-to-end loop the way a host trainer drives the API: double-buffered staging, the batch of step i is copied
+    # host->device and step i is enqueued, THEN the loss of step i-1 is read (its D2H copy has had a whole step to
+    # land), so the device never idles on the host; every step's inputs cross PCIe and every step's loss is read on
+    # the host inside the timed region (the last one by e2e_drain, before the closing event).
+    stage = [torch.empty((RAYS, 12), dtype=torch.float32, device=dev) for _ in range(2)]
+    stats_host = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    pending = [False, False]
+    losses = []
+
+    def e2e_read(slot):
+        if pending[slot]:
+            done[slot].synchronize()
+            losses.append(float(stats_host[slot][0]) / (3.0 * RAYS))
+            pending[slot] = False
 
     def step_e2e(i):
+        slot = i & 1
         i = (i * 37) % nb
-        stage.copy_(host[i * RAYS:(i + 1) * RAYS], non_blocking=True)             # H2D of this step's batch
-        T.train_step(model, state, {"rays": Rays(stage[:, 0:3], stage[:, 3:6], stage[:, 6:9]),
-                                    "pixels": stage[:, 9:12]}, lr_of(state.step), sparsity_length=sp_len,
+        st = stage[slot]
+        st.copy_(host[i * RAYS:(i + 1) * RAYS], non_blocking=True)                # H2D of this step's batch
+        T.train_step(model, state, {"rays": Rays(st[:, 0:3], st[:, 3:6], st[:, 6:9]),
+                                    "pixels": st[:, 9:12]}, lr_of(state.step), sparsity_length=sp_len,
                      sparsity_radius=sp_rad)
-        stats_host.copy_(state.stats_raw, non_blocking=True)                      # D2H of the step's loss sums
-        torch.cuda.current_stream().synchronize()
-        return float(stats_host[0]) / (3.0 * RAYS)
+        stats_host[slot].copy_(state.stats_raw, non_blocking=True)                # D2H of the step's loss sums
+        done[slot].record()
+        pending[slot] = True
+        e2e_read(1 - slot)                                                        # host reads the previous step's loss
+
+    def e2e_drain():
+        e2e_read(0)
+        e2e_read(1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, first):
+    def timed(fn, first, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
             fn(first + i)
+        if drain:
+            drain()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -291,7 +313,10 @@ def main():
     # ---- end-to-end (host buffers) ----
     for i in range(W):
         step_e2e(K + W + i)
-    ms_e2e = timed(step_e2e, K + 2 * W)
+    e2e_drain()
+    n_before = len(losses)
+    ms_e2e = timed(step_e2e, K + 2 * W, e2e_drain)
+    assert len(losses) - n_before == K and all(np.isfinite(losses[n_before:])), "e2e loop must read every step's loss"
     if sampler:
         sampler.stop()
     # ---- per-kernel-class timing (CUDA events around every launch), separate short run ----
