@@ -166,12 +166,15 @@ __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.0f, 1.0
 template <int G>
 struct Marcher {
   unsigned pq0, pq1, pq2;
-  int pdepth;   // depth of the previous leaf, -1 = no previous sample
-  int path;     // lane k: node entered at level k (lane 0: root)
+  static constexpr int PW = G >= 8 ? 1 : 8 / G;   // path registers per lane: levels l, l+G, ... are cached
+  static constexpr int CACHED = G * PW;
+  int pdepth;     // depth of the previous leaf, -1 = no previous sample
+  int path[PW];   // lane l, register j: node entered at level l + j*G (level 0: root)
 
   __device__ __forceinline__ void init() {
     pdepth = -1;
-    path = 0;
+#pragma unroll
+    for (int j = 0; j < PW; ++j) path[j] = 0;
     pq0 = pq1 = pq2 = 0;
   }
 
@@ -194,8 +197,12 @@ struct Marcher {
       if (pdepth >= 0) {
         const unsigned diff = (q0 ^ pq0) | (q1 ^ pq1) | (q2 ^ pq2);
         const int c = diff ? __clz(int(diff << 9)) : 23;
-        s = min(min(c, pdepth), G - 1);
-        node = __shfl_sync(mask, path, s, G);
+        s = min(min(c, pdepth), CACHED - 1);
+        int sel = path[0];
+#pragma unroll
+        for (int j = 1; j < PW; ++j)
+          if (s / G == j) sel = path[j];
+        node = __shfl_sync(mask, sel, s % G, G);
       }
       pq0 = q0;
       pq1 = q1;
@@ -212,7 +219,11 @@ struct Marcher {
           break;
         }
         node += skip;
-        if (l == k + 1) path = node;
+        if (l == (k + 1) % G) {
+#pragma unroll
+          for (int j = 0; j < PW; ++j)
+            if ((k + 1) / G == j) path[j] = node;
+        }
       }
       if (leaf) {
         pdepth = k;
@@ -430,7 +441,7 @@ __device__ __forceinline__ bool fetch_ray(const RaySrc& S, const TreeDev& T, Ray
     out_index = i;
     return true;
   }
-  constexpr int TW = 4, TH = RPB / 4;
+  constexpr int TW = RPB >= 64 ? 8 : 4, TH = RPB / TW;
   const int W = int(S.cam.width);
   const int tiles_x = (W + TW - 1) / TW;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -692,9 +703,11 @@ int opts_dev(const char* where, const pob_octree_opts* o, Opts& O) {
   return 0;
 }
 
-// Group width / coefficients per lane.  Default: 8 lanes per ray (twice the rays in flight of 16 lanes at the same
-// occupancy; the march is latency bound), lane l owns basis functions l, l+8, ...  POB_OCTREE_G=16|32 selects the
-// one-coefficient-per-lane mappings (profiling).
+// Group width / coefficients per lane.  Default: 4 lanes per ray (the march is instruction-issue bound and every
+// lane of a group repeats the walk, so fewer lanes per ray = fewer instructions per ray; lane l owns basis functions
+// l, l+4, ...).  Measured 800x800 / depth-8 SH16: 16 lanes 4.1 ms, 8 lanes 2.25 ms, 4 lanes 1.65 ms.
+// (2 lanes: 1.52 ms render but 4.7 ms training pass — not kept.)  POB_OCTREE_G=8|16|32 selects the other
+// mappings (profiling).
 int group_width(int K) {
   static int env = -1;
   if (env < 0) {
@@ -703,13 +716,18 @@ int group_width(int K) {
   }
   if (env == 32) return 32;
   if (env == 16) return K > 16 ? 32 : 16;
-  return 8;
+  if (env == 8) return 8;
+  return 4;
 }
 
 #define POB_OCTREE_DISPATCH(KERNEL, G, K, ...)                                   \
   do {                                                                           \
     if ((G) == 32) KERNEL<32, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);           \
     else if ((G) == 16) KERNEL<16, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);      \
+    else if ((G) == 4 && (K) <= 4) KERNEL<4, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);   \
+    else if ((G) == 4 && (K) <= 12) KERNEL<4, 3><<<blocks, 256, 0, st>>>(__VA_ARGS__);  \
+    else if ((G) == 4 && (K) <= 16) KERNEL<4, 4><<<blocks, 256, 0, st>>>(__VA_ARGS__);  \
+    else if ((G) == 4) KERNEL<4, 7><<<blocks, 256, 0, st>>>(__VA_ARGS__);               \
     else if ((K) <= 8) KERNEL<8, 1><<<blocks, 256, 0, st>>>(__VA_ARGS__);        \
     else if ((K) <= 16) KERNEL<8, 2><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
     else KERNEL<8, 4><<<blocks, 256, 0, st>>>(__VA_ARGS__);                      \
@@ -742,8 +760,8 @@ int ray_src(const char* where, const float* o, const float* d, const float* v, l
   S.row0 = row0;
   S.nrows = nrows;
   S.n = (long long)nrows * W;
-  const int th = rpb / 4;
-  blocks = unsigned(((W + 3) / 4) * ((nrows + th - 1) / th));
+  const int tw = rpb >= 64 ? 8 : 4, th = rpb / tw;
+  blocks = unsigned(((W + tw - 1) / tw) * ((nrows + th - 1) / th));
   return 0;
 }
 
