@@ -572,16 +572,26 @@ __global__ void octree_sgd_kernel(float* __restrict__ data, float* __restrict__ 
   const long long stride = (long long)gridDim.x * blockDim.x;
   float4* d4 = reinterpret_cast<float4*>(data);
   float4* g4 = reinterpret_cast<float4*>(grad);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 g = g4[i];
-    if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) {
-      float4 d = d4[i];
-      d.x = d.x - lr * g.x;
-      d.y = d.y - lr * g.y;
-      d.z = d.z - lr * g.z;
-      d.w = d.w - lr * g.w;
-      d4[i] = d;
-      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // four independent 16-byte gradient loads in flight per thread (the pass is a pure HBM stream)
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      g[u] = i < n4 ? __ldcs(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (g[u].x != 0.f || g[u].y != 0.f || g[u].z != 0.f || g[u].w != 0.f) {
+        float4 d = d4[i];
+        d.x = d.x - lr * g[u].x;
+        d.y = d.y - lr * g[u].y;
+        d.z = d.z - lr * g[u].z;
+        d.w = d.w - lr * g[u].w;
+        d4[i] = d;
+        g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -846,7 +856,7 @@ int pob_octree_sgd_step(float* data_dev, float* grad_dev, int64_t n, float lr, v
     return pob_fail(W, "data / grad must be 16-byte aligned");
   if (n == 0) return 0;
   pob_count_launch();
-  octree_sgd_kernel<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(data_dev, grad_dev, n, lr);
+  octree_sgd_kernel<<<sms * 16, 256, 0, (cudaStream_t)stream>>>(data_dev, grad_dev, n, lr);
   POB_CUDA(W, cudaGetLastError());
   return 0;
 }

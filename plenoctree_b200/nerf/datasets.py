@@ -1,0 +1,118 @@
+"""Blender-format dataset (nerf_sh/nerf/datasets.py:58-232, octree/nerf/datasets.py same classes) with the ray pool
+resident on the GPU: images and per-pixel rays are built once on the host with the reference expressions
+(`generate_rays`, white-background compositing, INTER_AREA half-resolution for factor 2), moved to HBM, and training
+batches are drawn on the device (one random image + `batch_size` random pixels with replacement, datasets.py:159-166,
+or pixels from all images with `image_batching`, :152-158).  The reference feeds batches through a host thread and a
+3-deep queue (datasets.py:63-118); with the pool in HBM no host->device traffic is left on the training path.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from .models import Rays
+from .utils import generate_rays
+
+
+class Blender:
+    def __init__(self, split, args, device="cuda", rank=0, world=1):
+        if getattr(args, "render_path", False):
+            raise ValueError("render_path cannot be used for the blender dataset.")
+        self.split = split
+        self.device = torch.device(device)
+        self.batch_size = int(args.batch_size) // world
+        self.image_batching = bool(args.image_batching)
+        self._load_renderings(args)
+        rays = generate_rays(self.w, self.h, self.focal, self.camtoworlds)   # [n,h,w,3] x3 (utils.py:545-589)
+        self.n_examples = self.images.shape[0]
+        n, hw = self.n_examples, self.h * self.w
+        self.rays_np = rays
+        if split == "train":
+            self.pixels = torch.from_numpy(self.images.reshape(n, hw, 3)).to(self.device)
+            self.rays = Rays(*[torch.from_numpy(np.ascontiguousarray(r.reshape(n, hw, 3))).to(self.device) for r in rays])
+            self.gen = torch.Generator(device=self.device)
+            self.gen.manual_seed(20201473 + rank)            # np.random.seed(20201473 + host_id), train.py:128
+        self.it = 0
+
+    # datasets.py:189-232
+    def _load_renderings(self, args):
+        from PIL import Image
+        with open(os.path.join(args.data_dir, f"transforms_{self.split}.json"), "r") as fp:
+            meta = json.load(fp)
+        images, cams = [], []
+        for frame in meta["frames"]:
+            fname = os.path.join(args.data_dir, frame["file_path"] + ".png")
+            image = np.array(Image.open(fname), dtype=np.float32) / 255.0
+            if args.factor == 2:
+                import cv2
+                image = cv2.resize(image, (image.shape[1] // 2, image.shape[0] // 2), interpolation=cv2.INTER_AREA)
+            elif args.factor > 0:
+                raise ValueError(f"Blender dataset only supports factor=0 or 2, {args.factor} set.")
+            cams.append(frame["transform_matrix"])
+            if image.shape[-1] == 4:
+                if args.white_bkgd:
+                    mask = image[..., -1:]
+                    image = image[..., :3] * mask + (1.0 - mask)
+                else:
+                    image = image[..., :3]
+            images.append(image[..., :3])
+        self.images = np.stack(images, axis=0).astype(np.float32)
+        self.h, self.w = self.images.shape[1:3]
+        self.resolution = self.h * self.w
+        self.camtoworlds = np.stack(cams, axis=0).astype(np.float32)
+        self.focal = 0.5 * self.w / np.tan(0.5 * float(meta["camera_angle_x"]))
+
+    @property
+    def size(self):
+        return self.n_examples
+
+    def __len__(self):
+        return self.n_examples
+
+    def next_train(self):
+        """{"pixels": [B,3], "rays": Rays([B,3] x3)} on the device (datasets.py:148-168)."""
+        B, hw, n = self.batch_size, self.h * self.w, self.n_examples
+        if self.image_batching:
+            idx = torch.randint(0, n * hw, (B,), device=self.device, generator=self.gen)
+            img, pix = idx // hw, idx % hw
+        else:
+            img = torch.randint(0, n, (1,), device=self.device, generator=self.gen).expand(B)
+            pix = torch.randint(0, hw, (B,), device=self.device, generator=self.gen)
+        return {"pixels": self.pixels[img, pix], "rays": Rays(*[r[img, pix] for r in self.rays])}
+
+    def next_test(self):
+        """{"pixels": [h,w,3], "rays": Rays([h,w,3] x3)} as numpy (datasets.py:170-182)."""
+        idx = self.it
+        self.it = (self.it + 1) % self.n_examples
+        return {"pixels": self.images[idx], "rays": Rays(*[r[idx] for r in self.rays_np])}
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return self.next_train() if self.split == "train" else self.next_test()
+
+
+def get_dataset(split, args, **kw):
+    """datasets.get_dataset (nerf_sh/nerf/datasets.py:39-40)."""
+    if args.dataset != "blender":
+        raise NotImplementedError(f"dataset {args.dataset!r}: only the Blender format is loaded here")
+    return Blender(split, args, **kw)
+
+
+def write_blender_scene(data_dir, images_by_split, poses_by_split, camera_angle_x):
+    """Write a scene in the Blender (NeRF-synthetic) layout: transforms_<split>.json + <split>/r_<i>.png (RGBA with
+    alpha 1).  Used to build synthetic scenes from a teacher model where no dataset can be downloaded."""
+    from PIL import Image
+    os.makedirs(data_dir, exist_ok=True)
+    for split, images in images_by_split.items():
+        os.makedirs(os.path.join(data_dir, split), exist_ok=True)
+        frames = []
+        for i, (im, c2w) in enumerate(zip(images, poses_by_split[split])):
+            rgba = np.concatenate([np.clip(im, 0, 1), np.ones_like(im[..., :1])], axis=-1)
+            Image.fromarray((rgba * 255.0 + 0.5).astype(np.uint8), mode="RGBA").save(
+                os.path.join(data_dir, split, f"r_{i}.png"))
+            frames.append({"file_path": f"./{split}/r_{i}", "transform_matrix": np.asarray(c2w, dtype=np.float64).tolist()})
+        with open(os.path.join(data_dir, f"transforms_{split}.json"), "w") as fp:
+            json.dump({"camera_angle_x": float(camera_angle_x), "frames": frames}, fp)

@@ -107,3 +107,44 @@ def eval_points(model, points, chunk=720720, to_cpu=False, coarse=False, precisi
 def compute_psnr(mse):
     """utils.compute_psnr (nerf_sh/nerf/utils.py:384-393)."""
     return -10.0 * np.log(mse) / np.log(10.0)
+
+
+def compute_ssim(img0, img1, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03, return_map=False,
+                 padding="valid"):
+    """utils.compute_ssim: mean SSIM of two [H,W,C] images with the separable 11-tap Gaussian window and clipped
+    (co)variances.  The reference has two border conventions: the JAX side convolves "valid"
+    (nerf_sh/nerf/utils.py:396-466, used by nerf_sh.train / eval), its torch twin zero-pads to "same"
+    (octree/nerf/utils.py:322-400, used by octree evaluation; golden-pinned in tests/golden/ssim.npz)."""
+    import torch
+    import torch.nn.functional as F
+    a = torch.as_tensor(img0, dtype=torch.float32)
+    b = torch.as_tensor(img1, dtype=torch.float32).to(a.device)
+    hw = filter_size // 2
+    shift = (2 * hw - filter_size + 1) / 2
+    f_i = ((torch.arange(filter_size, dtype=torch.float32, device=a.device) - hw + shift) / filter_sigma) ** 2
+    filt = torch.exp(-0.5 * f_i)
+    filt = filt / filt.sum()
+
+    def blur(z):                                  # [H,W,C] -> valid separable blur
+        z = z.permute(2, 0, 1)[:, None]           # [C,1,H,W]
+        ph = filter_size // 2 if padding == "same" else 0
+        z = F.conv2d(z, filt[None, None, None, :], padding=[0, ph])
+        z = F.conv2d(z, filt[None, None, :, None], padding=[ph, 0])
+        return z[:, 0].permute(1, 2, 0)
+
+    mu0, mu1 = blur(a), blur(b)
+    mu00, mu11, mu01 = mu0 * mu0, mu1 * mu1, mu0 * mu1
+    sigma00 = torch.clamp(blur(a * a) - mu00, min=0.0)
+    sigma11 = torch.clamp(blur(b * b) - mu11, min=0.0)
+    sigma01 = blur(a * b) - mu01
+    sigma01 = torch.sign(sigma01) * torch.minimum(torch.sqrt(sigma00 * sigma11), torch.abs(sigma01))
+    c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
+    ssim_map = ((2 * mu01 + c1) * (2 * sigma01 + c2)) / ((mu00 + mu11 + c1) * (sigma00 + sigma11 + c2))
+    return ssim_map if return_map else ssim_map.mean()
+
+
+def save_img(img, pth):
+    """utils.save_img (nerf_sh/nerf/utils.py:469-480): float image in [0,1] ([H,W,3] or [H,W]) -> PNG."""
+    from PIL import Image
+    arr = img.detach().cpu().numpy() if hasattr(img, "detach") else np.asarray(img)
+    Image.fromarray((np.clip(arr, 0.0, 1.0) * 255.0).astype(np.uint8)).save(pth, "PNG")

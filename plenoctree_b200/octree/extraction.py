@@ -14,6 +14,7 @@ outside the scope of this path and raise NotImplementedError.
 """
 import ctypes
 import math
+import os
 import types
 
 import numpy as np
@@ -182,3 +183,81 @@ def extract(args, nerf, dataset):
     if args.output:
         tree.save(args.output, compress=False)
     return tree
+
+
+# ---- `python -m plenoctree_b200.octree.extraction` (octree/extraction.py:60-176,425-516) ---------------------------------
+def _define_cli_flags():
+    from ..nerf import flags as F
+    F.define_flags()
+    F.define({
+        "output": ("string", "./tree.npz", "Output file"),
+        "center": ("string", "0 0 0", "Center of volume in x y z OR single number"),
+        "radius": ("string", "1.5", "1/2 side length of volume"),
+        "alpha_thresh": ("float", 0.01, "Alpha threshold to keep a voxel in initial sigma thresholding"),
+        "max_refine_prop": ("float", 0.5, "Max proportion of cells to refine"),
+        "z_min": ("float", None, "Discard z axis points below this value, for NDC use"),
+        "z_max": ("float", None, "Discard z axis points above this value, for NDC use"),
+        "tree_branch_n": ("integer", 2, "Tree branch factor (2=octree)"),
+        "init_grid_depth": ("integer", 8, "Initial evaluation grid (2^{x+1} voxel grid)"),
+        "samples_per_cell": ("integer", 8, "Samples per cell in step 2 (3D antialiasing)"),
+        "is_jaxnerf_ckpt": ("bool", False, "Whether the ckpt is from jaxnerf or not."),
+        "masking_mode": ("string", "weight", "How to calculate mask when building the octree (sigma | weight)"),
+        "weight_thresh": ("float", 0.001, "Weight threshold to keep a voxel"),
+        "projection_samples": ("integer", 10000, "Number of rays to sample for SH projection."),
+        "bbox_from_data": ("bool", False, "Use bounding box from dataset if possible"),
+        "data_bbox_scale": ("float", 1.0, "Scaling factor to apply to the bounding box from dataset"),
+        "autoscale": ("bool", False, "Automatic scaling, after bbox_from_data"),
+        "bbox_cube": ("bool", False, "Force bbox to be a cube"),
+        "bbox_scale": ("float", 1.0, "Scaling factor to apply to the bounding box at the end"),
+        "scale_alpha_thresh": ("float", 0.01, "Alpha threshold for autoscale"),
+        "eval": ("bool", True, "Evaluate after building the octree"),
+    })
+    return F
+
+
+def load_nerf(FLAGS, device):
+    """models.get_model_state(FLAGS, restore=True) of the octree side (octree/nerf/models.py:38-49): torch *.ckpt, or
+    a flax-format checkpoint_<step> with --is_jaxnerf_ckpt."""
+    from ..nerf import checkpoints, models
+    margs = type("A", (), dict(sh_deg=FLAGS.sh_deg, num_coarse_samples=FLAGS.num_coarse_samples,
+                               num_fine_samples=FLAGS.num_fine_samples, near=FLAGS.near, far=FLAGS.far,
+                               white_bkgd=FLAGS.white_bkgd, lindisp=FLAGS.lindisp, batch_size=min(FLAGS.chunk, 8192),
+                               sparsity_npoints=0, train_dir=None))
+    nerf, _ = models.get_model_state(margs, device=device, restore=False)
+    ok = (checkpoints.restore_model_state_from_jaxnerf(FLAGS.train_dir, nerf) if FLAGS.is_jaxnerf_ckpt
+          else checkpoints.restore_model_state(FLAGS.train_dir, nerf))
+    if not ok:
+        raise ValueError(f"no checkpoint found in {FLAGS.train_dir}")
+    return nerf
+
+
+def main(unused_argv):
+    from ..nerf import datasets
+    F = _define_cli_flags()
+    FLAGS = F.FLAGS
+    F.update_flags(FLAGS)
+    F.check_scope(FLAGS)
+    if FLAGS.bbox_from_data:
+        raise NotImplementedError("bbox_from_data needs an NSVF dataset (outside the scope of this path)")
+    torch.manual_seed(20200823)
+    dev = torch.device("cuda")
+    nerf = load_nerf(FLAGS, dev)
+    assert FLAGS.data_dir  # Dataset is required now (extraction.py:455)
+    dataset = datasets.get_dataset("train", FLAGS, device=dev)
+    base_dir = os.path.dirname(FLAGS.output)
+    if base_dir:
+        os.makedirs(base_dir, exist_ok=True)
+    tree = extract(FLAGS, nerf, dataset)
+    print(tree)
+    if FLAGS.eval:
+        from .evaluation import eval_octree
+        test = datasets.get_dataset("test", FLAGS, device=dev)
+        psnr, ssim = eval_octree(tree, test, FLAGS)
+        print("Average PSNR", psnr, "SSIM", ssim)
+    return tree
+
+
+if __name__ == "__main__":
+    from absl import app
+    _define_cli_flags()
+    app.run(main)

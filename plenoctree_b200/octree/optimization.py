@@ -96,3 +96,58 @@ def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=prin
     if not args.nosave and best_t is not None and args.output:
         best_t.save(args.output, compress=False)
     return best_t, best_validation_psnr
+
+
+# ---- `python -m plenoctree_b200.octree.optimization` (octree/optimization.py:56-133,134-248) -----------------------------
+def _define_cli_flags():
+    from ..nerf import flags as F
+    F.define_flags()
+    F.define({
+        "input": ("string", "./tree.npz", "Input octree npz from extraction.py"),
+        "output": ("string", "./tree_opt.npz", "Output octree npz"),
+        "render_interval": ("integer", 0, "render interval"),
+        "val_interval": ("integer", 2, "validation interval"),
+        "num_epochs": ("integer", 80, "epochs to train for"),
+        "sgd": ("bool", True, "use SGD optimizer instead of Adam"),
+        "lr": ("float", 1e7, "optimizer step size"),
+        "sgd_momentum": ("float", 0.0, "sgd momentum"),
+        "sgd_nesterov": ("bool", False, "sgd nesterov momentum?"),
+        "split_train": ("bool", None, "If specified, splits train set instead of loading val set"),
+        "split_holdout_prop": ("float", 0.2, "Proportion of images to hold out if split_train is set"),
+        "nosave": ("bool", False, "If set, does not save (for speed)"),
+        "continue_on_decrease": ("bool", False, "If set, continues training even if validation PSNR decreases"),
+    })
+    return F
+
+
+def main(unused_argv):
+    from ..nerf import datasets
+    F = _define_cli_flags()
+    FLAGS = F.FLAGS
+    F.update_flags(FLAGS)
+    torch.manual_seed(20200823)
+    np.random.seed(20200823)
+    dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+
+    def get_data(stage):
+        ds = datasets.get_dataset(stage, FLAGS, device=dev)
+        return ds.focal, [c for c in ds.camtoworlds], [torch.from_numpy(im).to(dev) for im in ds.images]
+
+    focal, train_c2w, train_gt = get_data("train")
+    if FLAGS.split_train:
+        test_sz = int(len(train_c2w) * FLAGS.split_holdout_prop)
+        perm = torch.randperm(len(train_c2w)).tolist()
+        test_c2w, test_gt = [train_c2w[i] for i in perm[:test_sz]], [train_gt[i] for i in perm[:test_sz]]
+        train_c2w, train_gt = [train_c2w[i] for i in perm[test_sz:]], [train_gt[i] for i in perm[test_sz:]]
+    else:
+        test_focal, test_c2w, test_gt = get_data("val")
+        assert focal == test_focal
+    tree = N3Tree.load(FLAGS.input, map_location=dev)
+    return optimize(FLAGS, tree, train_c2w, train_gt, test_c2w, test_gt, focal)
+
+
+if __name__ == "__main__":
+    from absl import app
+    _define_cli_flags()
+    app.run(main)

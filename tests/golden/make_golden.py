@@ -111,20 +111,6 @@ def gen_rays():
     print("rays.npz")
 
 
-if __name__ == "__main__":
-    torch.manual_seed(20200823)
-    torch.set_num_threads(8)
-    gen_eval_points(3, 2048, 20200823, "eval_points_sh16.npz")
-    gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
-    gen_eval_sh()
-    gen_posenc()
-    gen_ckpt_bridge()
-    try:
-        gen_rays()
-    except Exception as e:  # octree/nerf/utils.py pulls optional deps
-        print("rays.npz skipped:", repr(e))
-
-
 def gen_ckpt_bridge():
     """Let the REFERENCE's own loader (octree/nerf/models.py:66-113 restore_model_state_from_jaxnerf) consume a
     flax-format checkpoint written by plenoctree_b200.nerf.checkpoints.  flax is not installed, so the one call the
@@ -177,3 +163,29 @@ def gen_ckpt_bridge():
                         sums=np.array([float(sd[k].double().sum()) for k in keys]),
                         abs_sums=np.array([float(sd[k].double().abs().sum()) for k in keys]))
     print("ckpt_bridge.npz", len(keys), "tensors,", len(blob), "bytes")
+
+
+def gen_ssim():
+    """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
+    ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
+    rs = np.random.RandomState(21)
+    a = rs.uniform(0, 1, size=(40, 36, 3)).astype(np.float32)
+    b = np.clip(a + rs.normal(0, 0.1, size=a.shape), 0, 1).astype(np.float32)
+    val = float(ref_utils.compute_ssim(torch.from_numpy(a), torch.from_numpy(b), max_val=1.0))
+    np.savez_compressed(os.path.join(HERE, "ssim.npz"), a=a, b=b, ssim=val)
+    print("ssim.npz", val)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(20200823)
+    torch.set_num_threads(8)
+    gen_eval_points(3, 2048, 20200823, "eval_points_sh16.npz")
+    gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
+    gen_eval_sh()
+    gen_posenc()
+    gen_ckpt_bridge()
+    gen_ssim()
+    try:
+        gen_rays()
+    except Exception as e:  # octree/nerf/utils.py pulls optional deps
+        print("rays.npz skipped:", repr(e))

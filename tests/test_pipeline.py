@@ -1,0 +1,169 @@
+"""End-to-end drop-in flow on a synthetic Blender-format scene (no dataset can be downloaded here), through the CLI
+mains with the reference's flag names and a YAML config:
+
+    nerf_sh.train -> checkpoint_<step> (flax format) -> nerf_sh.eval -> octree.extraction --is_jaxnerf_ckpt
+    -> tree.npz -> octree.optimization -> tree_opt.npz -> octree.evaluation
+
+CPU part: flags / YAML / dataset loader / SSIM golden.  GPU part: the whole chain on 48x48 images."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+def _set_flags(**kw):
+    from plenoctree_b200.nerf import flags as F
+    F.define_flags()
+    if not F.FLAGS.is_parsed():
+        F.FLAGS.mark_as_parsed()
+    for k, v in kw.items():
+        setattr(F.FLAGS, k, v)
+    return F.FLAGS
+
+
+def test_flags_yaml_and_scope(tmp_path):
+    from plenoctree_b200.nerf import flags as F
+    FLAGS = _set_flags(train_dir=str(tmp_path), data_dir=str(tmp_path), use_viewdirs=True, sh_deg=-1, batch_size=1024,
+                       config=None)
+    cfg = tmp_path / "blender.yaml"
+    cfg.write_text("dataset: blender\nimage_batching: false\nfactor: 0\nnum_coarse_samples: 64\nnum_fine_samples: 128\n"
+                   "use_viewdirs: false\nwhite_bkgd: true\nbatch_size: 1024\nsh_deg: 3\nrandomized: true\n"
+                   "max_steps: 2000000\n")     # = nerf_sh/config/blender.yaml of the reference
+    FLAGS.config = str(tmp_path / "blender")
+    F.update_flags(FLAGS)
+    assert FLAGS.sh_deg == 3 and FLAGS.use_viewdirs is False and FLAGS.max_steps == 2000000 and FLAGS.factor == 0
+    F.check_flags(FLAGS, world=8)
+    F.check_scope(FLAGS)
+    with pytest.raises(ValueError):
+        F.check_flags(FLAGS, world=3)                      # batch 1024 not divisible by 3 devices (utils.py:252)
+    (tmp_path / "bad.yaml").write_text("not_a_flag: 1\n")
+    FLAGS.config = str(tmp_path / "bad")
+    with pytest.raises(ValueError, match="Invalid args"):
+        F.update_flags(FLAGS)
+    FLAGS.config = None
+    FLAGS.use_viewdirs = True
+    with pytest.raises(NotImplementedError):
+        F.check_scope(FLAGS)
+    FLAGS.use_viewdirs = False
+
+
+def test_ssim_matches_reference_torch_twin(golden_dir):
+    from plenoctree_b200.nerf.utils import compute_ssim
+    z = np.load(os.path.join(golden_dir, "ssim.npz"))
+    assert abs(float(compute_ssim(z["a"], z["b"], padding="same")) - float(z["ssim"])) < 1e-6
+    same = float(compute_ssim(z["a"], z["a"]))
+    assert abs(same - 1.0) < 1e-6
+    assert float(compute_ssim(z["a"], z["b"])) < 1.0        # "valid" borders (JAX side)
+
+
+def test_blender_loader_cpu(tmp_path):
+    from plenoctree_b200.nerf import datasets as D
+    from plenoctree_b200.nerf.utils import generate_rays, pose_spherical
+    rs = np.random.RandomState(0)
+    poses = [pose_spherical(30.0 * i, -30.0, 4.0) for i in range(3)]
+    ims = [rs.uniform(0, 1, size=(10, 12, 3)).astype(np.float32) for _ in range(3)]
+    D.write_blender_scene(str(tmp_path), {"test": ims}, {"test": poses}, 0.6911112070083618)
+    args = type("A", (), dict(data_dir=str(tmp_path), factor=0, white_bkgd=True, batch_size=64, image_batching=False,
+                              dataset="blender", render_path=False))
+    ds = D.get_dataset("test", args, device="cpu")
+    assert ds.size == 3 and (ds.h, ds.w) == (10, 12)
+    assert abs(ds.focal - 0.5 * 12 / np.tan(0.5 * 0.6911112070083618)) < 1e-4
+    assert np.abs(ds.images - np.stack(ims)).max() <= 1.0 / 255.0 + 1e-6           # 8-bit PNG round trip
+    b = ds.next_test()
+    want = generate_rays(12, 10, ds.focal, np.stack(poses)[:1])
+    assert np.array_equal(b["rays"].directions, want.directions[0]) and b["pixels"].shape == (10, 12, 3)
+    with open(os.path.join(str(tmp_path), "transforms_test.json")) as f:
+        assert len(json.load(f)["frames"]) == 3
+
+
+@pytest.mark.gpu
+def test_cli_chain_train_eval_extract_optimize(tmp_path):
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf import datasets as D
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf.utils import generate_rays, pose_spherical, render_image
+    from plenoctree_b200.nerf_sh import eval as EV, train as TR
+    from plenoctree_b200.octree import evaluation as OE, extraction as EX, optimization as OP
+    from plenoctree_b200.octree import N3Tree
+    # ---- synthetic scene: views of a teacher NeRF-SH field (random weights, density head scaled up) ----
+    sh_deg, W = 3, 48
+    ft = np.concatenate([O.init_flat_params(sh_deg, 7001, bias_scale=0.05), O.init_flat_params(sh_deg, 7002, bias_scale=0.05)])
+    P = O.param_count(sh_deg)
+    for m in range(2):
+        off = m * P + P - 48 - 1 - 256 * 48 - 256
+        ft[off:off + 256] *= 30.0
+    teacher = NerfModel(sh_deg=sh_deg, max_rays=4096)
+    teacher.set_params(ft)
+    cam_x = 0.6911112070083618
+    focal = 0.5 * W / np.tan(0.5 * cam_x)
+    rs = np.random.RandomState(3)
+    splits = {"train": 8, "val": 2, "test": 2}
+    poses = {k: [pose_spherical(rs.uniform(-180, 180), rs.uniform(-80, -10), 4.0) for _ in range(n)] for k, n in splits.items()}
+    images = {}
+    for k in splits:
+        rays = generate_rays(W, W, focal, np.stack(poses[k]))
+        images[k] = [render_image(teacher, Rays(rays.origins[i], rays.directions[i], rays.viewdirs[i]))[0].cpu().numpy()
+                     for i in range(splits[k])]
+    data_dir, train_dir = str(tmp_path / "scene"), str(tmp_path / "ckpt")
+    D.write_blender_scene(data_dir, images, poses, cam_x)
+    (tmp_path / "cfg.yaml").write_text("dataset: blender\nfactor: 0\nnum_coarse_samples: 64\nnum_fine_samples: 128\n"
+                                       "use_viewdirs: false\nwhite_bkgd: true\nbatch_size: 1024\nsh_deg: 3\n"
+                                       "randomized: true\nmax_steps: 300\n")
+    EX._define_cli_flags()
+    OP._define_cli_flags()
+    FLAGS = _set_flags(train_dir=train_dir, data_dir=data_dir, config=str(tmp_path / "cfg"), save_every=300,
+                       print_every=100, render_every=0, sparsity_npoints=1000, lr_init=2e-3, lr_final=2e-4, chunk=4096,
+                       noise_std=None, image_batching=True)
+    # ---- nerf_sh.train / nerf_sh.eval ----
+    model, state = TR.main(None)
+    assert os.path.exists(os.path.join(train_dir, "checkpoint_300")) and state.step == 300
+    psnr, ssim = EV.main(None)
+    assert os.path.exists(os.path.join(train_dir, "test_preds", "000.png"))
+    assert float(open(os.path.join(train_dir, "test_preds", "psnr.txt")).read()) == pytest.approx(psnr)
+    fresh = NerfModel(sh_deg=sh_deg, max_rays=4096)
+    fresh.init_params(20200823)
+    rays = generate_rays(W, W, focal, np.stack(poses["test"]))
+    gt = torch.from_numpy(images["test"][0]).cuda()
+    p_init = -10 * np.log10(float(((render_image(fresh, Rays(rays.origins[0], rays.directions[0], rays.viewdirs[0]))[0] - gt) ** 2).mean()))
+    assert psnr > p_init + 2.0, (p_init, psnr)          # 300 steps on 8 tiny views: it learns
+    # resuming continues from the checkpoint's step and Adam state
+    FLAGS.config = None          # the YAML would re-apply max_steps: 300 (update_flags overrides, like the reference)
+    FLAGS.max_steps = 310
+    FLAGS.save_every = 10
+    _, state2 = TR.main(None)
+    assert state2.step == 310 and os.path.exists(os.path.join(train_dir, "checkpoint_310"))
+    # ---- octree.extraction (flax-format checkpoint) ----
+    FLAGS.is_jaxnerf_ckpt = True
+    FLAGS.init_grid_depth = 5
+    FLAGS.samples_per_cell = 8
+    FLAGS.masking_mode = "sigma"      # 8 views of 48x48 rays are too sparse for the weight mask (tests/test_octree.py covers it)
+    FLAGS.alpha_thresh = 0.01
+    FLAGS.renderer_step_size = 1e-3
+    FLAGS.radius = "1.5"
+    FLAGS.output = str(tmp_path / "tree.npz")
+    FLAGS.eval = False
+    tree = EX.main(None)
+    assert os.path.exists(FLAGS.output) and tree.max_depth == 5
+    test_ds = D.get_dataset("test", FLAGS, device="cuda")
+    p_tree, s_tree = OE.eval_octree(tree, test_ds, FLAGS)
+    # the 64^3 tree of a field trained for 300 steps is a coarse stand-in; it must still beat the untrained model
+    assert p_tree > p_init + 1.0 and np.isfinite(s_tree), (p_init, psnr, p_tree)
+    # ---- octree.optimization ----
+    FLAGS.input = FLAGS.output
+    FLAGS.output = str(tmp_path / "tree_opt.npz")
+    FLAGS.num_epochs = 6
+    FLAGS.val_interval = 2
+    FLAGS.lr = 1e7 * (W * W) / (800.0 * 800.0) / 4
+    FLAGS.continue_on_decrease = True
+    best, p_val = OP.main(None)
+    if best is not None:
+        assert os.path.exists(FLAGS.output)
+        t2 = N3Tree.load(FLAGS.output)
+        p_opt, _ = OE.eval_octree(t2, test_ds, FLAGS)
+        assert p_opt > p_tree - 0.5, (p_tree, p_opt)
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "pipeline.json"), "w") as f:
+        json.dump({"psnr_nerf_init": p_init, "psnr_nerf_300_steps": psnr, "ssim_nerf": ssim, "psnr_tree": p_tree,
+                   "psnr_tree_val_after_opt": p_val, "tree_nodes": int(tree.n_internal)}, f, indent=1)
