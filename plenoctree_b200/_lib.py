@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplenoctree_b200.so")
+LIB_PATH = os.environ.get("POB_LIB_PATH") or os.path.join(_HERE, "libplenoctree_b200.so")   # override: kernel A/B experiments
 
 PREC_FP16 = 1
 PREC_FP16X3 = 3

@@ -22,6 +22,13 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef POB_FWD_DEFER_CHUNKS
+#define POB_FWD_DEFER_CHUNKS 4
+#endif
+#ifndef POB_FWD_DEFER_PACE_NS
+#define POB_FWD_DEFER_PACE_NS 0
+#endif
+
 namespace pob {
 
 namespace {
@@ -333,6 +340,8 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         uint8_t* const h_glob = saving ? p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES : nullptr;
         uint32_t maskw[8];
         constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
+        constexpr int DEFER_CH = (SAVE && NSPLIT == 1) ? POB_FWD_DEFER_CHUNKS : 0;
+        uint32_t defer[DEFER_CH > 0 ? DEFER_CH * 16 : 1];
         uint32_t va[32], vb[32];
         tmem_ld32(d_tmem + c_begin * 32, va);
 #pragma unroll
@@ -359,9 +368,18 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
             const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
                                  ((unit ^ uint32_t(row & 7)) << 4);
             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (saving)   // T layout: [32-row group][8-column unit][row][16 B] -> 512 contiguous bytes per warp store
-              *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
-                  make_uint4(w[0], w[1], w[2], w[3]);
+            if (saving) {   // T layout: [32-row group][8-column unit][row][16 B] -> 512 contiguous bytes per warp store
+              if (cc < NCH - DEFER_CH) {
+                *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
+                    make_uint4(w[0], w[1], w[2], w[3]);
+              } else {
+                // the last DEFER_CH chunks wait in registers and are stored after the tile has been handed to the
+                // MMA warp: the store stream then overlaps the next layer's MMAs (HBM otherwise idles through
+                // every MMA phase, because a write-back L2 drains only when new stores push it)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) defer[(cc - (NCH - DEFER_CH)) * 16 + u * 4 + i] = w[i];
+              }
+            }
             if (NSPLIT == 3) {
               uint32_t wl[4];
 #pragma unroll
@@ -387,6 +405,21 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         }
         signal_a_ready();
         trace_stamp(trp, trole, tn);             // a_ready signalled
+        if (saving && DEFER_CH > 0) {
+#pragma unroll
+          for (int dc = 0; dc < DEFER_CH; ++dc) {
+            const int c = c_begin + NCH - DEFER_CH + dc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
+                  make_uint4(defer[dc * 16 + u * 4], defer[dc * 16 + u * 4 + 1], defer[dc * 16 + u * 4 + 2],
+                             defer[dc * 16 + u * 4 + 3]);
+#if POB_FWD_DEFER_PACE_NS > 0
+              __nanosleep(POB_FWD_DEFER_PACE_NS);   // pace the deferred stream under the weight stream (L2 throughput cap)
+#endif
+            }
+          }
+        }
         if (l == SKIP_LAYER) {
           // E is dead until the next iteration: encode the next tile now, in the shadow of the
           // layer-6/7/heads MMAs.
