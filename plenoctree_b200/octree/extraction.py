@@ -39,13 +39,33 @@ def default_args(**kw):
     return a
 
 
-def _grid_sigmas(nerf, reso, offset, scale, world=1, rank=0):
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _grid_sigmas(nerf, reso, offset, scale):
     """the chunked eval_points_raw loop over the dense grid (extraction.py:262-274 / 308-320) as one sweep whose
-    voxel centres are generated in the kernel; returns sigma [reso^3] x-major (this rank's x-slab when world > 1)."""
+    voxel centres are generated in the kernel; returns sigma [reso^3] x-major.  With torch.distributed initialised
+    every rank sweeps its x-slab (voxel slabs, no collective in the sweep) and the slabs are all-gathered
+    once so that every rank can build the (replicated) tree."""
+    import torch.distributed as dist
+    rank, world = _rank_world()
     x0, nx = ops.grid_slab(reso, rank, world)
     _, sig = ops.eval_grid(nerf._blob(False), nerf.sh_deg, reso, offset, scale, x0=x0, nx=nx, want_rgb=False,
                            precision=nerf.precision, device=nerf.device)
-    return sig
+    if world == 1:
+        return sig
+    slabs = [ops.grid_slab(reso, r, world) for r in range(world)]
+    if len({n for _, n in slabs}) == 1:
+        full = torch.empty(reso * reso * reso, dtype=torch.float32, device=nerf.device)
+        dist.all_gather_into_tensor(full, sig.contiguous())
+        return full
+    parts = [torch.empty(n * reso * reso, dtype=torch.float32, device=nerf.device) for _, n in slabs]
+    dist.all_gather(parts, sig.contiguous())
+    return torch.cat(parts)
 
 
 def calculate_grid_weights(dataset, sigmas, reso, invradius, offset, step_size=1e-4, cam_chunk=4096):
@@ -142,15 +162,29 @@ def step2(args, tree, nerf, cells_per_launch=None):
         raise NotImplementedError("vanilla-NeRF SH projection (use_viewdirs) is outside the scope of this path")
     if tree.data_format.format != 1:
         raise NotImplementedError("step 2 is implemented for SH trees (the RGBA alpha-weighted mean is not built)")
+    import torch.distributed as dist
     S = int(args.samples_per_cell)
     leaf_ind = torch.where(tree.depths == tree.max_depth)[0]
     if cells_per_launch is None:
         cells_per_launch = max(1, (1 << 22) // S)
-    for i in range(0, leaf_ind.shape[0], cells_per_launch):
+    rank, world = _rank_world()
+    n = int(leaf_ind.shape[0])
+    out = torch.zeros((n, tree.data_dim), dtype=torch.float32, device=tree.device)
+    gen = torch.Generator(device=tree.device)
+    # leaf chunks are dealt round-robin to the ranks (contiguous leaf ranges, no collective inside); each chunk draws
+    # its sample positions from its own seed, so the tree does not depend on the number of ranks
+    for cid, i in enumerate(range(0, n, cells_per_launch)):
+        if cid % world != rank:
+            continue
         chunk_inds = leaf_ind[i:i + cells_per_launch]
-        points = tree[chunk_inds].sample(S)
-        rgba = ops.eval_cells_mean(nerf._blob(False), nerf.sh_deg, points.contiguous(), S, precision=nerf.precision)
-        tree[chunk_inds] = rgba
+        gen.manual_seed(20200823 + cid)
+        u = torch.rand((chunk_inds.shape[0], S, 3), device=tree.device, generator=gen)
+        points = tree[chunk_inds].sample(S, uniforms=u)
+        out[i:i + cells_per_launch] = ops.eval_cells_mean(nerf._blob(False), nerf.sh_deg, points.contiguous(), S,
+                                                          precision=nerf.precision)
+    if world > 1:
+        dist.all_reduce(out)          # every row was written by exactly one rank
+    tree[leaf_ind] = out
 
 
 def extract(args, nerf, dataset):

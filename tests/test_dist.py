@@ -111,3 +111,55 @@ def test_octree_epoch_two_ranks_equals_one_rank():
     for rank, psnr2, data in res:
         assert abs(psnr2 - psnr1) < 1e-3, (rank, psnr1, psnr2)
         assert np.abs(data - want).max() <= 1e-4 * np.abs(want).max(), rank
+
+
+def _extract_tree(cells_per_launch):
+    import numpy as np
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf.models import NerfModel
+    from plenoctree_b200.octree import N3Tree, extraction as E
+    sh_deg = 3
+    flat = O.init_flat_params(sh_deg, 20200823, bias_scale=0.05)
+    nerf = NerfModel(sh_deg=sh_deg)
+    nerf.set_params(np.concatenate([flat, flat]))
+    args = E.default_args(init_grid_depth=4, samples_per_cell=4, masking_mode="sigma", alpha_thresh=1e-4, output=None)
+    tree = N3Tree(N=2, data_dim=49, init_reserve=4096, geom_resize_fact=1.0, depth_limit=4, radius=[1.5] * 3,
+                  center=[0.0] * 3, data_format="SH16")
+    E.step1(args, tree, nerf, None)
+    E.step2(args, tree, nerf, cells_per_launch=cells_per_launch)
+    n = tree.n_internal
+    return tree.child[:n].cpu().numpy(), tree.data[:n].cpu().numpy()
+
+
+def _extract_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # both ranks share cuda:0 (see _octree_worker)
+    try:
+        torch.cuda.set_device(0)
+        child, data = _extract_tree(500)
+        q.put((rank, child, data))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_extraction_two_ranks_equals_one_rank():
+    """C4 sharding: x-slabs of the grid sweep and leaf chunks of step 2 split over ranks must give the
+    same tree as one process (per-chunk sample seeds make step 2 independent of the world size)."""
+    import numpy as np
+    child1, data1 = _extract_tree(500)
+    assert child1.shape[0] > 100 and np.abs(data1).max() > 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_extract_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, child, data in res:
+        assert np.array_equal(child, child1), rank
+        # identical sample positions; the per-cell mean is accumulated with float atomics (order-dependent rounding)
+        assert np.abs(data - data1).max() <= 1e-5 * np.abs(data1).max(), rank

@@ -438,8 +438,9 @@ def test_extraction_end_to_end_matches_oracle(tmp_path):
     # -- step 2: finest leaves hold the mean of [raw_rgb, relu-ed raw_sigma-mean] over their samples
     lv = otree.leaves()
     deep = np.nonzero(otree.leaf_depths(lv) == L)[0]
-    torch.manual_seed(0)
-    u = torch.rand((deep.size, 4, 3), device="cuda").cpu().numpy()  # the draw step2 made (single launch)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(20200823)   # step2 seeds leaf chunk c with 20200823 + c; this tree is a single chunk
+    u = torch.rand((deep.size, 4, 3), device="cuda", generator=gen).cpu().numpy()
     spts = otree.sample(lv[deep], 4, u).reshape(-1, 3)
     with torch.no_grad():
         rgb_o, s_o = O.eval_points_raw(O.unflatten(flat, sh_deg), torch.from_numpy(spts))
