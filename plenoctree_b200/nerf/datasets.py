@@ -1,4 +1,5 @@
-"""Blender-format dataset (nerf_sh/nerf/datasets.py:58-232, octree/nerf/datasets.py same classes) with the ray pool
+"""Blender- and NSVF-format datasets (nerf_sh/nerf/datasets.py:58-232,491-552; octree/nerf/datasets.py same classes,
+plus bbox.txt :72-78) with the ray pool
 resident on the GPU: images and per-pixel rays are built once on the host with the reference expressions
 (`generate_rays`, white-background compositing, INTER_AREA half-resolution for factor 2), moved to HBM, and training
 batches are drawn on the device (one random image + `batch_size` random pixels with replacement, datasets.py:159-166,
@@ -15,11 +16,13 @@ from .models import Rays
 from .utils import generate_rays
 
 
-class Blender:
+class Dataset:
     def __init__(self, split, args, device="cuda", rank=0, world=1):
         if getattr(args, "render_path", False):
-            raise ValueError("render_path cannot be used for the blender dataset.")
+            raise ValueError("render_path cannot be used for this dataset.")
         self.split = split
+        bbox_path = os.path.join(os.path.expanduser(args.data_dir), "bbox.txt")      # octree/nerf/datasets.py:72-78
+        self.bbox = np.loadtxt(bbox_path)[:-1] if os.path.isfile(bbox_path) else None
         self.device = torch.device(device)
         self.batch_size = int(args.batch_size) // world
         self.image_batching = bool(args.image_batching)
@@ -35,33 +38,8 @@ class Blender:
             self.gen.manual_seed(20201473 + rank)            # np.random.seed(20201473 + host_id), train.py:128
         self.it = 0
 
-    # datasets.py:189-232
     def _load_renderings(self, args):
-        from PIL import Image
-        with open(os.path.join(args.data_dir, f"transforms_{self.split}.json"), "r") as fp:
-            meta = json.load(fp)
-        images, cams = [], []
-        for frame in meta["frames"]:
-            fname = os.path.join(args.data_dir, frame["file_path"] + ".png")
-            image = np.array(Image.open(fname), dtype=np.float32) / 255.0
-            if args.factor == 2:
-                import cv2
-                image = cv2.resize(image, (image.shape[1] // 2, image.shape[0] // 2), interpolation=cv2.INTER_AREA)
-            elif args.factor > 0:
-                raise ValueError(f"Blender dataset only supports factor=0 or 2, {args.factor} set.")
-            cams.append(frame["transform_matrix"])
-            if image.shape[-1] == 4:
-                if args.white_bkgd:
-                    mask = image[..., -1:]
-                    image = image[..., :3] * mask + (1.0 - mask)
-                else:
-                    image = image[..., :3]
-            images.append(image[..., :3])
-        self.images = np.stack(images, axis=0).astype(np.float32)
-        self.h, self.w = self.images.shape[1:3]
-        self.resolution = self.h * self.w
-        self.camtoworlds = np.stack(cams, axis=0).astype(np.float32)
-        self.focal = 0.5 * self.w / np.tan(0.5 * float(meta["camera_angle_x"]))
+        raise NotImplementedError
 
     @property
     def size(self):
@@ -94,11 +72,88 @@ class Blender:
         return self.next_train() if self.split == "train" else self.next_test()
 
 
+class Blender(Dataset):
+    # datasets.py:189-232
+    def _load_renderings(self, args):
+        from PIL import Image
+        with open(os.path.join(args.data_dir, f"transforms_{self.split}.json"), "r") as fp:
+            meta = json.load(fp)
+        images, cams = [], []
+        for frame in meta["frames"]:
+            fname = os.path.join(args.data_dir, frame["file_path"] + ".png")
+            image = np.array(Image.open(fname), dtype=np.float32) / 255.0
+            if args.factor == 2:
+                import cv2
+                image = cv2.resize(image, (image.shape[1] // 2, image.shape[0] // 2), interpolation=cv2.INTER_AREA)
+            elif args.factor > 0:
+                raise ValueError(f"Blender dataset only supports factor=0 or 2, {args.factor} set.")
+            cams.append(frame["transform_matrix"])
+            if image.shape[-1] == 4:
+                if args.white_bkgd:
+                    mask = image[..., -1:]
+                    image = image[..., :3] * mask + (1.0 - mask)
+                else:
+                    image = image[..., :3]
+            images.append(image[..., :3])
+        self.images = np.stack(images, axis=0).astype(np.float32)
+        self.h, self.w = self.images.shape[1:3]
+        self.resolution = self.h * self.w
+        self.camtoworlds = np.stack(cams, axis=0).astype(np.float32)
+        self.focal = 0.5 * self.w / np.tan(0.5 * float(meta["camera_angle_x"]))
+
+
+class NSVF(Dataset):
+    """NSVF generic dataset (nerf_sh/nerf/datasets.py:491-552): intrinsics.txt, pose/<split>_*.txt, rgb/<split>_*.png
+    with split prefixes 0_ train / 1_ val / 2_ test (1_ when there is no 2_), camera flip diag(1,-1,-1,1)."""
+
+    def _load_renderings(self, args):
+        from PIL import Image
+        d = os.path.expanduser(args.data_dir)
+        K = np.loadtxt(os.path.join(d, "intrinsics.txt"))
+        pose_files = sorted(os.listdir(os.path.join(d, "pose")))
+        img_files = sorted(os.listdir(os.path.join(d, "rgb")))
+        pick = lambda files, pre: [x for x in files if x.startswith(pre)]
+        if self.split == "train":
+            pose_files, img_files = pick(pose_files, "0_"), pick(img_files, "0_")
+        elif self.split == "val":
+            pose_files, img_files = pick(pose_files, "1_"), pick(img_files, "1_")
+        elif self.split == "test":
+            tp, ti = pick(pose_files, "2_"), pick(img_files, "2_")
+            if len(tp) == 0:
+                tp, ti = pick(pose_files, "1_"), pick(img_files, "1_")
+            pose_files, img_files = tp, ti
+        assert len(img_files) == len(pose_files)
+        cam_trans = np.diag(np.array([1, -1, -1, 1], dtype=np.float32))
+        images, cams = [], []
+        for img_fname, pose_fname in zip(img_files, pose_files):
+            image = np.array(Image.open(os.path.join(d, "rgb", img_fname)), dtype=np.float32) / 255.0
+            cams.append(np.loadtxt(os.path.join(d, "pose", pose_fname)) @ cam_trans)
+            if image.shape[-1] == 4:
+                if args.white_bkgd:
+                    mask = image[..., -1:]
+                    image = image[..., :3] * mask + (1.0 - mask)
+                else:
+                    image = image[..., :3]
+            if args.factor > 1:
+                import cv2
+                image = cv2.resize(image, (image.shape[1] // args.factor, image.shape[0] // args.factor),
+                                   interpolation=cv2.INTER_AREA)
+            images.append(image[..., :3])
+        self.images = np.stack(images, axis=0).astype(np.float32)
+        self.h, self.w = self.images.shape[1:3]
+        self.resolution = self.h * self.w
+        self.camtoworlds = np.stack(cams, axis=0).astype(np.float32)
+        self.focal = (K[0, 0] + K[1, 1]) * 0.5          # fx and fy assumed equal
+        if args.factor > 1:
+            self.focal /= args.factor
+
+
 def get_dataset(split, args, **kw):
     """datasets.get_dataset (nerf_sh/nerf/datasets.py:39-40)."""
-    if args.dataset != "blender":
-        raise NotImplementedError(f"dataset {args.dataset!r}: only the Blender format is loaded here")
-    return Blender(split, args, **kw)
+    classes = {"blender": Blender, "nsvf": NSVF}
+    if args.dataset not in classes:
+        raise NotImplementedError(f"dataset {args.dataset!r}: the Blender and NSVF formats are loaded here (LLFF/NDC is not)")
+    return classes[args.dataset](split, args, **kw)
 
 
 def write_blender_scene(data_dir, images_by_split, poses_by_split, camera_angle_x):
@@ -116,3 +171,22 @@ def write_blender_scene(data_dir, images_by_split, poses_by_split, camera_angle_
             frames.append({"file_path": f"./{split}/r_{i}", "transform_matrix": np.asarray(c2w, dtype=np.float64).tolist()})
         with open(os.path.join(data_dir, f"transforms_{split}.json"), "w") as fp:
             json.dump({"camera_angle_x": float(camera_angle_x), "frames": frames}, fp)
+
+
+def write_nsvf_scene(data_dir, images_by_split, poses_by_split, focal, bbox=None):
+    """Write a scene in the NSVF layout (intrinsics.txt, pose/, rgb/, optional bbox.txt); poses are the c2w matrices
+    the loader should return (the on-disk files carry the inverse camera flip)."""
+    from PIL import Image
+    os.makedirs(os.path.join(data_dir, "pose"), exist_ok=True)
+    os.makedirs(os.path.join(data_dir, "rgb"), exist_ok=True)
+    h, w = next(iter(images_by_split.values()))[0].shape[:2]
+    K = np.array([[focal, 0, w * 0.5, 0], [0, focal, h * 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)
+    np.savetxt(os.path.join(data_dir, "intrinsics.txt"), K)
+    flip = np.diag([1.0, -1.0, -1.0, 1.0])
+    for split, pre in (("train", "0_"), ("val", "1_"), ("test", "2_")):
+        for i, (im, c2w) in enumerate(zip(images_by_split.get(split, []), poses_by_split.get(split, []))):
+            Image.fromarray((np.clip(im, 0, 1) * 255.0 + 0.5).astype(np.uint8), mode="RGB").save(
+                os.path.join(data_dir, "rgb", f"{pre}{i:04d}.png"))
+            np.savetxt(os.path.join(data_dir, "pose", f"{pre}{i:04d}.txt"), np.asarray(c2w, dtype=np.float64) @ flip)
+    if bbox is not None:
+        np.savetxt(os.path.join(data_dir, "bbox.txt"), np.asarray(list(bbox) + [0.4], dtype=np.float64)[None])

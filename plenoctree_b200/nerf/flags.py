@@ -117,8 +117,8 @@ def check_scope(args):
         raise NotImplementedError("use_viewdirs (vanilla NeRF colour head) is outside the NeRF-SH path")
     if args.sg_dim > 0:
         raise NotImplementedError("spherical gaussians (sg_dim) are outside the NeRF-SH path")
-    if args.dataset != "blender":
-        raise NotImplementedError(f"dataset {args.dataset!r}: only the Blender format is loaded here")
+    if args.dataset not in ("blender", "nsvf"):
+        raise NotImplementedError(f"dataset {args.dataset!r}: the Blender and NSVF formats are loaded here (LLFF/NDC is not)")
     if (args.net_depth, args.net_width, args.skip_layer, args.min_deg_point, args.max_deg_point) != (8, 256, 4, 0, 10):
         raise NotImplementedError("the fused kernel is built for the 8x256 trunk, skip 4, posenc degrees 0..10")
     if (args.net_activation, args.rgb_activation, args.sigma_activation) != ("relu", "sigmoid", "relu"):

@@ -192,12 +192,17 @@ def extract(args, nerf, dataset):
     if args.sg_dim > 0:
         raise NotImplementedError("SG trees are outside the scope of this path")
     data_format = f"SH{(args.sh_deg + 1) ** 2}" if args.sh_deg > 0 else None
-    center = list(map(float, str(args.center).split()))
-    if len(center) == 1:
-        center *= 3
-    radius = list(map(float, str(args.radius).split()))
-    if len(radius) == 1:
-        radius *= 3
+    if getattr(args, "bbox_from_data", False):            # extraction.py:458-462 (NSVF bbox.txt)
+        assert getattr(dataset, "bbox", None) is not None  # Dataset must be NSVF
+        center = ((dataset.bbox[:3] + dataset.bbox[3:6]) * 0.5).tolist()
+        radius = ((dataset.bbox[3:6] - dataset.bbox[:3]) * 0.5 * args.data_bbox_scale).tolist()
+    else:
+        center = list(map(float, str(args.center).split()))
+        if len(center) == 1:
+            center *= 3
+        radius = list(map(float, str(args.radius).split()))
+        if len(radius) == 1:
+            radius *= 3
     if args.autoscale:
         center, radius = auto_scale(args, center, radius, nerf)
     radius = [r * args.bbox_scale for r in radius]
@@ -271,8 +276,6 @@ def main(unused_argv):
     FLAGS = F.FLAGS
     F.update_flags(FLAGS)
     F.check_scope(FLAGS)
-    if FLAGS.bbox_from_data:
-        raise NotImplementedError("bbox_from_data needs an NSVF dataset (outside the scope of this path)")
     torch.manual_seed(20200823)
     dev = torch.device("cuda")
     nerf = load_nerf(FLAGS, dev)

@@ -167,3 +167,34 @@ def test_cli_chain_train_eval_extract_optimize(tmp_path):
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "pipeline.json"), "w") as f:
         json.dump({"psnr_nerf_init": p_init, "psnr_nerf_300_steps": psnr, "ssim_nerf": ssim, "psnr_tree": p_tree,
                    "psnr_tree_val_after_opt": p_val, "tree_nodes": int(tree.n_internal)}, f, indent=1)
+
+
+def test_nsvf_loader_and_tt_config_cpu(tmp_path):
+    """nerf_sh/config/tt.yaml selects `dataset: nsvf` (BASELINE configs[2]); the loader honours the split prefixes,
+    the camera flip and bbox.txt (extraction --bbox_from_data)."""
+    from plenoctree_b200.nerf import datasets as D, flags as F
+    from plenoctree_b200.nerf.utils import pose_spherical
+    rs = np.random.RandomState(1)
+    poses = {"train": [pose_spherical(40.0 * i, -20.0, 2.5) for i in range(3)], "val": [pose_spherical(10.0, -60.0, 2.5)]}
+    ims = {k: [rs.uniform(0, 1, size=(9, 16, 3)).astype(np.float32) for _ in v] for k, v in poses.items()}
+    D.write_nsvf_scene(str(tmp_path / "scene"), ims, poses, focal=20.0, bbox=[-1, -2, -3, 1, 2, 3])
+    (tmp_path / "tt.yaml").write_text("dataset: nsvf\nimage_batching: false\nfactor: 0\nnum_coarse_samples: 64\n"
+                                      "num_fine_samples: 128\nuse_viewdirs: false\nwhite_bkgd: true\nbatch_size: 1024\n"
+                                      "randomized: true\nsh_deg: 4\nmax_steps: 2000000\nnear: 0.0\nfar: 4.0\n"
+                                      "sparsity_radius: 5.0\nsparsity_length: 0.2\n")   # = nerf_sh/config/tt.yaml
+    FLAGS = _set_flags(train_dir=str(tmp_path), data_dir=str(tmp_path / "scene"), config=str(tmp_path / "tt"))
+    F.update_flags(FLAGS)
+    F.check_scope(FLAGS)
+    assert (FLAGS.dataset, FLAGS.sh_deg, FLAGS.far, FLAGS.sparsity_radius) == ("nsvf", 4, 4.0, 5.0)
+    tr = D.get_dataset("train", FLAGS, device="cpu")
+    te = D.get_dataset("test", FLAGS, device="cpu")          # no 2_ files: falls back to the 1_ (val) images
+    assert tr.size == 3 and te.size == 1 and (tr.h, tr.w) == (9, 16) and tr.focal == 20.0
+    assert np.allclose(tr.camtoworlds, np.stack(poses["train"]), atol=1e-6)
+    assert np.allclose(te.camtoworlds[0], poses["val"][0], atol=1e-6)
+    assert np.allclose(tr.bbox, [-1, -2, -3, 1, 2, 3])
+    b = tr.next_train()
+    assert b["pixels"].shape == (1024, 3) and b["rays"].origins.shape == (1024, 3)
+    FLAGS.config = None
+    FLAGS.dataset = "blender"
+    FLAGS.sh_deg = 3
+    FLAGS.near, FLAGS.far, FLAGS.sparsity_radius, FLAGS.sparsity_length = 2.0, 6.0, 1.5, 0.05
