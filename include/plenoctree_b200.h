@@ -262,6 +262,11 @@ int pob_octree_train_persp(const pob_octree* tree, const pob_octree_opts* opts, 
  * data -= lr * grad; grad = 0, touching only entries whose gradient is non-zero. */
 int pob_octree_sgd_step(float* data_dev, float* grad_dev, int64_t n, float lr, void* stream);
 
+/* torch.optim.Adam(lr, eps) (betas 0.9 / 0.999, no weight decay; octree/optimization.py:190-193, the `--nosgd` branch)
+ * fused with zero_grad: m, v are the caller's moment buffers (same shape as data), `step` = updates already applied. */
+int pob_octree_adam_step(float* data_dev, float* grad_dev, float* m_dev, float* v_dev, int64_t n, float lr, float step,
+                         float eps, void* stream);
+
 /* N3Tree.__getitem__(points): packed leaf index node*N^3 + (i*N + j)*N + k of the leaf holding each world
  * point (points clamped into the volume like svox). */
 int pob_octree_query(const pob_octree* tree, const float* points_dev, int64_t n, int64_t* leaf_index_dev,

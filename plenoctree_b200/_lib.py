@@ -48,6 +48,7 @@ SIGNATURES = {
     "pob_octree_render_backward": (_i, [_vp, _vp, _fp, _fp, _fp, _i64, _vp, _i, _i, _fp, _fp, _vp]),
     "pob_octree_train_persp": (_i, [_vp, _vp, _vp, _i, _i, _fp, _c.c_float, _fp, _vp, _fp, _vp]),
     "pob_octree_sgd_step": (_i, [_fp, _fp, _i64, _c.c_float, _vp]),
+    "pob_octree_adam_step": (_i, [_fp, _fp, _fp, _fp, _i64, _c.c_float, _c.c_float, _c.c_float, _vp]),
     "pob_octree_query": (_i, [_vp, _fp, _i64, _vp, _vp]),
     "pob_grid_weight_render": (_i, [_fp, _i, _vp, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
                                     _vp, _fp, _vp, _vp]),

@@ -861,6 +861,20 @@ int pob_octree_sgd_step(float* data_dev, float* grad_dev, int64_t n, float lr, v
   return 0;
 }
 
+int pob_octree_adam_step(float* data_dev, float* grad_dev, float* m_dev, float* v_dev, int64_t n, float lr, float step,
+                         float eps, void* stream) {
+  const char* W = "pob_octree_adam_step";
+  if (!data_dev || !grad_dev || !m_dev || !v_dev) return pob_fail(W, "NULL pointer");
+  if (n < 0) return pob_fail(W, "negative size");
+  if (pob_sm_count_cached() <= 0) return pob_fail(W, "no sm_100 CUDA device (there is no CPU fallback)");
+  if (n == 0) return 0;
+  pob_count_launch();
+  POB_CUDA(W, pob::launch_adam(data_dev, grad_dev, m_dev, v_dev, n, lr, step, 0.9f, 0.999f, eps, 1.0f, 0.0f,
+                               (cudaStream_t)stream));
+  POB_CUDA(W, cudaMemsetAsync(grad_dev, 0, size_t(n) * sizeof(float), (cudaStream_t)stream));
+  return 0;
+}
+
 int pob_octree_query(const pob_octree* tree, const float* points_dev, int64_t n, int64_t* leaf_index_dev,
                      void* stream) {
   const char* W = "pob_octree_query";

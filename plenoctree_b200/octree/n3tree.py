@@ -217,6 +217,17 @@ class N3Tree:
         n = self.n_internal * self.N ** 3 * self.data_dim
         check(lib.pob_octree_sgd_step(ptr(self.data), ptr(g), n, float(lr), stream_ptr()))
 
+    @torch.no_grad()
+    def adam_step(self, lr, eps=1e-8):
+        """torch.optim.Adam(lr, eps).step() + zero_grad (octree/optimization.py:190-193; eps 1e-4 for fp16 trees)."""
+        g = self.grad_buffer()
+        if getattr(self, "_adam", None) is None or self._adam[0].shape != self.data.shape:
+            self._adam = [torch.zeros_like(self.data), torch.zeros_like(self.data), 0]
+        n = self.n_internal * self.N ** 3 * self.data_dim
+        check(lib.pob_octree_adam_step(ptr(self.data), ptr(g), ptr(self._adam[0]), ptr(self._adam[1]), n, float(lr),
+                                       float(self._adam[2]), float(eps), stream_ptr()))
+        self._adam[2] += 1
+
     # ---- io -----------------------------------------------------------------------------------------
     def shrink_to_fit(self):
         n = self.n_internal

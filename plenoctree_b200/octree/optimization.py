@@ -7,8 +7,7 @@
     svox.N3Tree.load/save  optimization.py:168,245-248    plenoctree_b200.octree.N3Tree
 
 Multi-GPU: every image's pixel rows are split over the ranks, each rank scatters into its own
-dense gradient buffer, one NCCL all-reduce (SUM) per image joins them before the replicated SGD update.  The
-Adam branch of the reference (`--nosgd`) is not built (the shipped configs all use --sgd, octree/config/*.json).
+dense gradient buffer, one NCCL all-reduce (SUM) per image joins them before the replicated SGD update.  Both optimiser branches of the reference are fused with zero_grad: SGD (`--sgd`, all shipped configs) and Adam (`--nosgd`).
 """
 import math
 import types
@@ -53,7 +52,7 @@ def run_test_step(r, test_c2w, test_gt, H, W, focal):
     return tpsnr / max(len(test_c2w), 1)
 
 
-def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr):
+def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr, adam_eps=None):
     """one pass over the training images (optimization.py:216-229); returns the mean train PSNR."""
     import torch.distributed as dist
     rank, world = _rank_world()
@@ -63,7 +62,10 @@ def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr):
         r.train_persp(c2w, im_gt, W, H, focal, rows=rows if world > 1 else None, sq_err=sq[j:j + 1])
         if world > 1:
             dist.all_reduce(tree.grad_buffer()[:tree.n_internal])
-        tree.sgd_step(lr)
+        if adam_eps is None:
+            tree.sgd_step(lr)
+        else:
+            tree.adam_step(lr, adam_eps)
     if world > 1:
         dist.all_reduce(sq)
     mse = (sq / float(H * W * 3)).cpu().numpy()
@@ -72,9 +74,8 @@ def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr):
 
 def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=print):
     """optimization.py:134-248 without dataset/flag plumbing.  train_gt/test_gt: [n,H,W,3] float tensors."""
-    if not args.sgd:
-        raise NotImplementedError("the Adam branch of octree.optimization is not built")
-    if args.sgd_momentum != 0.0 or args.sgd_nesterov:
+    adam_eps = None if args.sgd else 1e-8      # optimization.py:190-193 (1e-4 only for fp16 trees)
+    if args.sgd and (args.sgd_momentum != 0.0 or args.sgd_nesterov):
         raise NotImplementedError("SGD momentum is not built (reference configs use momentum 0)")
     H, W = int(train_gt[0].shape[0]), int(train_gt[0].shape[1])
     r = VolumeRenderer(tree, step_size=args.renderer_step_size)
@@ -82,7 +83,7 @@ def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=prin
     log(f"** initial val psnr {best_validation_psnr}")
     best_t = None
     for i in range(args.num_epochs):
-        tpsnr = train_epoch(tree, r, train_c2w, train_gt, H, W, focal, args.lr)
+        tpsnr = train_epoch(tree, r, train_c2w, train_gt, H, W, focal, args.lr, adam_eps)
         log(f"** train_psnr {tpsnr}")
         if i % args.val_interval == args.val_interval - 1 or i == args.num_epochs - 1:
             validation_psnr = run_test_step(r, test_c2w, test_gt, H, W, focal)

@@ -485,3 +485,24 @@ def test_optimization_improves_psnr():
     print("\n".join(logs[-6:]))
     assert p1 > p0 + 1.0, (p0, p1)
     _record("optimization", {"psnr_before": p0, "psnr_after": p1})
+
+
+@pytest.mark.gpu
+def test_adam_step_matches_torch_adam():
+    """octree.optimization --nosgd (optimization.py:190-193): pob_octree_adam_step == torch.optim.Adam + zero_grad."""
+    import torch
+    otree = make_tree(71, 2, "SH9")
+    tree = to_device_tree(otree)
+    n = otree.n_internal
+    ref = torch.nn.Parameter(tree.data[:n].clone())
+    opt = torch.optim.Adam([ref], lr=0.05, eps=1e-8)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(3):
+        grad = torch.randn(ref.shape, device="cuda", generator=g) * (torch.rand(ref.shape, device="cuda", generator=g) < 0.3)
+        tree.grad_buffer()[:n] = grad
+        tree.adam_step(0.05, 1e-8)
+        ref.grad = grad.clone()
+        opt.step()
+        assert float(tree.grad_buffer().abs().max()) == 0.0
+    err = float((tree.data[:n] - ref.data).abs().max())
+    assert err < 1e-5, err
