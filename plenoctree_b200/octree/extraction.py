@@ -160,8 +160,7 @@ def step2(args, tree, nerf, cells_per_launch=None):
     `cells_per_launch` leaves (default: 2^22 points) instead of chunk // S = 320."""
     if args.use_viewdirs:
         raise NotImplementedError("vanilla-NeRF SH projection (use_viewdirs) is outside the scope of this path")
-    if tree.data_format.format != 1:
-        raise NotImplementedError("step 2 is implemented for SH trees (the RGBA alpha-weighted mean is not built)")
+    rgba_tree = tree.data_format.format == 0
     import torch.distributed as dist
     S = int(args.samples_per_cell)
     leaf_ind = torch.where(tree.depths == tree.max_depth)[0]
@@ -180,8 +179,20 @@ def step2(args, tree, nerf, cells_per_launch=None):
         gen.manual_seed(20200823 + cid)
         u = torch.rand((chunk_inds.shape[0], S, 3), device=tree.device, generator=gen)
         points = tree[chunk_inds].sample(S, uniforms=u)
-        out[i:i + cells_per_launch] = ops.eval_cells_mean(nerf._blob(False), nerf.sh_deg, points.contiguous(), S,
-                                                          precision=nerf.precision)
+        if not rgba_tree:
+            out[i:i + cells_per_launch] = ops.eval_cells_mean(nerf._blob(False), nerf.sh_deg, points.contiguous(), S,
+                                                              precision=nerf.precision)
+        else:
+            # RGBA trees (extraction.py:378-390): sigma = mean, rgb = alpha-weighted mean with alpha of a 2/reso step
+            rgb, sigma = nerf.eval_points_raw(points.reshape(-1, 3).contiguous())
+            rgb = rgb.reshape(-1, S, tree.data_dim - 1)
+            sigma = sigma.reshape(-1, S, 1)
+            approx_delta = 2.0 / (2 ** (args.init_grid_depth + 1))
+            alpha = 1.0 - torch.exp(-approx_delta * sigma)
+            msum = alpha.sum(dim=1)
+            rgb_avg = (rgb * alpha).sum(dim=1) / msum
+            rgb_avg[msum[..., 0] < 1e-3] = 0
+            out[i:i + cells_per_launch] = torch.cat([rgb_avg, sigma.mean(dim=1)], dim=-1)
     if world > 1:
         dist.all_reduce(out)          # every row was written by exactly one rank
     tree[leaf_ind] = out
