@@ -246,6 +246,7 @@ class N3Tree:
         t.parent_depth = self.parent_depth[:n].clone()
         t.grad = None
         t._leaves = None
+        t._adam = None
         return t
 
     def state(self):
