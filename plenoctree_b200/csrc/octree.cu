@@ -179,12 +179,13 @@ struct Marcher {
   }
 
   // leaf holding origin + t * dir; returns its flat index and the march length to its exit (+ step)
-  __device__ __forceinline__ long long locate(const TreeDev& T, const Ray& r, float step, float t, int l, unsigned mask,
-                                              float& delta_t) {
-    float pos[3], cube;
+  // (leaf indices fit 32 bits: n_nodes * N^3 < 2^32 is checked on the host)
+  __device__ __forceinline__ unsigned locate(const TreeDev& T, const Ray& r, float step, float t, int l, unsigned mask,
+                                             float& delta_t) {
+    float pos[3], cube, inv_cube = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) pos[a] = __fadd_rn(r.o[a], __fmul_rn(t, r.d[a]));
-    long long idx;
+    unsigned idx;
     bool pow2 = false;
     if (T.N == 2) {
       pow2 = true;
@@ -212,7 +213,7 @@ struct Marcher {
       bool leaf = false;
       for (; k <= 22; ++k) {
         const int sh = 22 - k;
-        idx = (long long)node * 8 + ((((q0 >> sh) & 1u) << 2) | (((q1 >> sh) & 1u) << 1) | ((q2 >> sh) & 1u));
+        idx = unsigned(node) * 8u + ((((q0 >> sh) & 1u) << 2) | (((q1 >> sh) & 1u) << 1) | ((q2 >> sh) & 1u));
         const int skip = __ldg(T.child + idx);
         if (skip == 0) {
           leaf = true;
@@ -227,7 +228,8 @@ struct Marcher {
       }
       if (leaf) {
         pdepth = k;
-        cube = __int_as_float((127 + k + 1) << 23);  // 2^(k+1)
+        cube = __int_as_float((127 + k + 1) << 23);       // 2^(k+1)
+        inv_cube = __int_as_float((127 - k - 1) << 23);   // 2^-(k+1), exact
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float sc = pos[a] * cube;
@@ -237,6 +239,7 @@ struct Marcher {
         // deeper than the 23 cached digits: finish with the plain walk from `node`
         pdepth = 22;
         cube = 8388608.0f;
+        pow2 = false;   // the exit length below falls back to the division
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float sc = pos[a] * cube;
@@ -252,19 +255,19 @@ struct Marcher {
             pos[a] = pos[a] - fl;
           }
           cube = cube * 2.0f;
-          idx = (long long)node * 8 + (u[0] * 4 + u[1] * 2 + u[2]);
+          idx = unsigned(node) * 8u + unsigned(u[0] * 4 + u[1] * 2 + u[2]);
           const int skip = __ldg(T.child + idx);
           if (skip == 0) break;
           node += skip;
         }
       }
     } else {
-      idx = query_leaf(T.child, T.N, pos, cube);
+      idx = unsigned(query_leaf(T.child, T.N, pos, cube));
     }
     float smin, smax;
     dda_unit(pos, r.invd, smin, smax);
     // cube is a power of two for N = 2: multiplying by its (exact) reciprocal equals the IEEE division
-    const float len = pow2 ? __fmul_rn(__fsub_rn(smax, smin), __frcp_rn(cube)) : __fsub_rn(smax, smin) / cube;
+    const float len = pow2 ? __fmul_rn(__fsub_rn(smax, smin), inv_cube) : __fsub_rn(smax, smin) / cube;
     delta_t = __fadd_rn(len, step);
     return idx;
   }
@@ -291,9 +294,9 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
   Marcher<G> m;
   m.init();
   float delta_t;
-  long long idx = m.locate(T, r, O.step, t, l, mask, delta_t);
+  unsigned idx = m.locate(T, r, O.step, t, l, mask, delta_t);
   for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
-    const float* __restrict__ val = T.data + idx * D;
+    const float* __restrict__ val = T.data + size_t(idx) * unsigned(D);
     const float sigma = __ldg(val + D - 1);
     float c0[KPL], c1[KPL], c2[KPL];  // lane l owns basis functions l, l+G, ...
 #pragma unroll
@@ -309,7 +312,7 @@ __device__ __forceinline__ void trace_forward(const TreeDev& T, const Opts& O, c
     const float t_next = t + delta_t;
     const bool more = t_next < r.tmax;
     float delta_n = 0.f;
-    long long idx_n = 0;
+    unsigned idx_n = 0;
     if (more) idx_n = m.locate(T, r, O.step, t_next, l, mask, delta_n);
     ++visits;
     if (sigma > O.sigma_thresh) {
@@ -363,9 +366,9 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
   Marcher<G> m;
   m.init();
   float delta_t;
-  long long idx = m.locate(T, r, O.step, t, l, mask, delta_t);
+  unsigned idx = m.locate(T, r, O.step, t, l, mask, delta_t);
   for (int it = 0; it < MAX_MARCH_STEPS; ++it) {
-    const float* __restrict__ val = T.data + idx * D;
+    const float* __restrict__ val = T.data + size_t(idx) * unsigned(D);
     const float sigma = __ldg(val + D - 1);
     float c0[KPL], c1[KPL], c2[KPL];  // lane l owns basis functions l, l+G, ...
 #pragma unroll
@@ -381,7 +384,7 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
     const float t_next = t + delta_t;
     const bool more = t_next < r.tmax;
     float delta_n = 0.f;
-    long long idx_n = 0;
+    unsigned idx_n = 0;
     if (more) idx_n = m.locate(T, r, O.step, t_next, l, mask, delta_n);
     if (sigma > 0.0f) {
       const float att = __expf(-delta_t * r.delta_scale * sigma);
@@ -397,7 +400,7 @@ __device__ __forceinline__ void trace_backward(const TreeDev& T, const Opts& O, 
       p1 = group_sum<G>(p1, mask);
       p2 = group_sum<G>(p2, mask);
       const float s0 = sigmoidf(p0), s1 = sigmoidf(p1), s2 = sigmoidf(p2);
-      float* gv = grad + idx * D;
+      float* gv = grad + size_t(idx) * unsigned(D);
       const float t0 = weight * s0 * (1.0f - s0) * g[0];
       const float t1 = weight * s1 * (1.0f - s1) * g[1];
       const float t2 = weight * s2 * (1.0f - s2) * g[2];
@@ -680,6 +683,7 @@ int tree_dev(const char* where, const pob_octree* t, TreeDev& T) {
   if (!t->data_dev || !t->child_dev) return pob_fail(where, "tree data/child pointer is NULL");
   if (t->N < 2 || t->N > 8) return pob_fail(where, "tree branch factor N must be in [2, 8]");
   if (t->n_nodes < 1) return pob_fail(where, "tree has no nodes");
+  if (double(t->n_nodes) * t->N * t->N * t->N >= 4294967296.0) return pob_fail(where, "tree too large (leaf index must fit 32 bits)");
   const int K = t->basis_dim;
   if (t->format == POB_OCTREE_RGBA) {
     if (K != 1 || t->data_dim != 4) return pob_fail(where, "RGBA trees have data_dim 4");
