@@ -135,7 +135,7 @@ pob::FwdParams pob_base_params(const void* packed, int sh_deg) { return base_par
 
 extern "C" {
 
-int pob_abi_version(void) { return 1; }
+int pob_abi_version(void) { return 2; }   // 2: pob_render_config grew sigma_noise_*_dev; octree entry points
 
 long long pob_launch_count(void) { return g_launches.load(); }
 
