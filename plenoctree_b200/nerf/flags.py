@@ -82,8 +82,18 @@ def define(table):
             _DEFINERS[kind](name, default, helptxt)
 
 
-def define_flags():
+# defaults that differ on the octree side of the reference (octree/nerf/utils.py:44-219 vs nerf_sh/nerf/utils.py:60-253)
+_OCTREE_DEFAULTS = {"chunk": 81920, "gc_every": 10000, "print_every": 500, "render_every": 10000, "save_every": 5000,
+                    "net_activation": "ReLU", "rgb_activation": "Sigmoid", "sigma_activation": "ReLU"}
+
+
+def define_flags(octree=False):
+    """nerf_sh side by default; octree=True applies the octree side's defaults (octree.extraction / optimization /
+    evaluation are separate programs in the reference, each with its own copy of define_flags)."""
     define(_COMMON)
+    if octree:
+        for name, value in _OCTREE_DEFAULTS.items():
+            FLAGS.set_default(name, value)
 
 
 def update_flags(args):
@@ -121,7 +131,8 @@ def check_scope(args):
         raise NotImplementedError(f"dataset {args.dataset!r}: the Blender and NSVF formats are loaded here (LLFF/NDC is not)")
     if (args.net_depth, args.net_width, args.skip_layer, args.min_deg_point, args.max_deg_point) != (8, 256, 4, 0, 10):
         raise NotImplementedError("the fused kernel is built for the 8x256 trunk, skip 4, posenc degrees 0..10")
-    if (args.net_activation, args.rgb_activation, args.sigma_activation) != ("relu", "sigmoid", "relu"):
+    if tuple(str(a).lower() for a in (args.net_activation, args.rgb_activation, args.sigma_activation)) != (
+            "relu", "sigmoid", "relu"):
         raise NotImplementedError("activations other than relu / sigmoid / relu")   # models.py:280-281 raise the same
     if args.legacy_posenc_order or args.render_path or args.spherify:
         raise NotImplementedError("legacy_posenc_order / render_path / spherify are outside the scope of this path")

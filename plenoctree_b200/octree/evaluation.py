@@ -33,7 +33,7 @@ def eval_octree(t, dataset, args, want_frames=False):
 
 def main(unused_argv):
     from ..nerf import datasets, flags as F
-    F.define_flags()
+    F.define_flags(octree=True)
     F.define({"input": ("string", "./tree.npz", "Input octree npz"),
               "write_images": ("string", None, "If specified, writes rendered images to this directory")})
     FLAGS = F.FLAGS

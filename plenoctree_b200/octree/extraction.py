@@ -238,7 +238,7 @@ def extract(args, nerf, dataset):
 # ---- `python -m plenoctree_b200.octree.extraction` (octree/extraction.py:60-176,425-516) ---------------------------------
 def _define_cli_flags():
     from ..nerf import flags as F
-    F.define_flags()
+    F.define_flags(octree=True)
     F.define({
         "output": ("string", "./tree.npz", "Output file"),
         "center": ("string", "0 0 0", "Center of volume in x y z OR single number"),

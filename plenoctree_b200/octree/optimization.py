@@ -102,7 +102,7 @@ def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=prin
 # ---- `python -m plenoctree_b200.octree.optimization` (octree/optimization.py:56-133,134-248) -----------------------------
 def _define_cli_flags():
     from ..nerf import flags as F
-    F.define_flags()
+    F.define_flags(octree=True)
     F.define({
         "input": ("string", "./tree.npz", "Input octree npz from extraction.py"),
         "output": ("string", "./tree_opt.npz", "Output octree npz"),
@@ -113,6 +113,7 @@ def _define_cli_flags():
         "lr": ("float", 1e7, "optimizer step size"),
         "sgd_momentum": ("float", 0.0, "sgd momentum"),
         "sgd_nesterov": ("bool", False, "sgd nesterov momentum?"),
+        "write_vid": ("string", None, "If specified, writes rendered video to given path (*.mp4)"),
         "split_train": ("bool", None, "If specified, splits train set instead of loading val set"),
         "split_holdout_prop": ("float", 0.2, "Proportion of images to hold out if split_train is set"),
         "nosave": ("bool", False, "If set, does not save (for speed)"),
@@ -126,6 +127,8 @@ def main(unused_argv):
     F = _define_cli_flags()
     FLAGS = F.FLAGS
     F.update_flags(FLAGS)
+    if FLAGS.write_vid:
+        raise NotImplementedError("write_vid (mp4 output) is outside the scope of this path")
     torch.manual_seed(20200823)
     np.random.seed(20200823)
     dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))

@@ -176,6 +176,28 @@ def gen_ssim():
     print("ssim.npz", val)
 
 
+def gen_flags():
+    """every flags.DEFINE_* of the reference's four flag tables (name -> [kind, default]), read from the source AST
+    (nerf_sh/nerf/utils.py imports jax at module level and cannot be imported here)."""
+    import ast
+    import json
+
+    def extract(path):
+        out = {}
+        for node in ast.walk(ast.parse(open(os.path.join(REF, path)).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("DEFINE_"):
+                try:
+                    out[ast.literal_eval(node.args[0])] = [node.func.attr[len("DEFINE_"):], ast.literal_eval(node.args[1])]
+                except Exception:
+                    continue
+        return out
+    res = {p: extract(p) for p in ("nerf_sh/nerf/utils.py", "octree/nerf/utils.py", "octree/extraction.py",
+                                   "octree/optimization.py")}
+    with open(os.path.join(HERE, "flags.json"), "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    print("flags.json", {k: len(v) for k, v in res.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(20200823)
     torch.set_num_threads(8)
@@ -185,6 +207,7 @@ if __name__ == "__main__":
     gen_posenc()
     gen_ckpt_bridge()
     gen_ssim()
+    gen_flags()
     try:
         gen_rays()
     except Exception as e:  # octree/nerf/utils.py pulls optional deps

@@ -198,3 +198,29 @@ def test_nsvf_loader_and_tt_config_cpu(tmp_path):
     FLAGS.dataset = "blender"
     FLAGS.sh_deg = 3
     FLAGS.near, FLAGS.far, FLAGS.sparsity_radius, FLAGS.sparsity_length = 2.0, 6.0, 1.5, 0.05
+
+
+def test_flag_tables_match_the_reference(golden_dir):
+    """tests/golden/flags.json = every flags.DEFINE_* of the reference (AST of nerf_sh/nerf/utils.py,
+    octree/nerf/utils.py, octree/extraction.py, octree/optimization.py): same names, kinds and defaults here."""
+    import re
+    from plenoctree_b200.nerf import flags as F
+    ref = json.load(open(os.path.join(golden_dir, "flags.json")))
+    kind_of = lambda k: "string" if k == "enum" else k
+    mine = F._COMMON
+    r = ref["nerf_sh/nerf/utils.py"]
+    assert len(r) >= 50
+    for name, (kind, default) in r.items():
+        assert name in mine, name
+        assert mine[name][0] == kind_of(kind) and mine[name][1] == default, (name, mine[name][:2], kind, default)
+    for name, (kind, default) in ref["octree/nerf/utils.py"].items():
+        assert name in mine, name
+        want = F._OCTREE_DEFAULTS.get(name, mine[name][1])
+        assert mine[name][0] == kind_of(kind) and want == default, (name, want, default)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mod, key in (("extraction", "octree/extraction.py"), ("optimization", "octree/optimization.py")):
+        src = open(os.path.join(root, "plenoctree_b200", "octree", mod + ".py")).read()
+        table = eval("{" + re.search(r"F\.define\(\{(.*?)\}\)", src, re.S).group(1) + "}")
+        assert set(table) == set(ref[key]), (mod, set(table) ^ set(ref[key]))
+        for name, (kind, default) in ref[key].items():
+            assert table[name][0] == kind_of(kind) and table[name][1] == default, (mod, name)
