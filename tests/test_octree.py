@@ -506,3 +506,66 @@ def test_adam_step_matches_torch_adam():
         assert float(tree.grad_buffer().abs().max()) == 0.0
     err = float((tree.data[:n] - ref.data).abs().max())
     assert err < 1e-5, err
+
+
+def test_n3tree_host_bookkeeping_on_cpu(tmp_path):
+    """The integer bookkeeping of plenoctree_b200.octree.N3Tree (refine order, chunked last level, leaf order, depths,
+    corners / sample, assignment, relu, npz round trip) run on CPU tensors: the one CUDA call it makes (leaf lookup,
+    pob_octree_query) is served by the oracle's query here; tests/-m gpu checks the real kernel against the same."""
+    import torch
+    from plenoctree_b200.octree import n3tree as NT
+    rs = np.random.RandomState(1)
+    L = 4
+    reso = 2 ** (L + 1)
+    mask = rs.rand(reso, reso, reso) < 0.08
+    radius, center = [1.5, 1.2, 1.0], [0.1, 0.0, -0.2]
+    otree, grid = OO.build_tree_from_grid(mask, L, radius, center, 49, "SH16", refine_chunk=700)
+    t = NT.N3Tree.__new__(NT.N3Tree)                      # the constructor insists on a CUDA device
+    t.device = torch.device("cpu")
+    t.N, t.data_dim, t.depth_limit, t.geom_resize_fact = 2, 49, L, 1.0
+    t.data_format = NT.DataFormat("SH16")
+    t.invradius = torch.from_numpy(otree.invradius.copy())
+    t.offset = torch.from_numpy(otree.offset.copy())
+    t.data = torch.zeros((16, 2, 2, 2, 49))
+    t.child = torch.zeros((16, 2, 2, 2), dtype=torch.int32)
+    t.parent_depth = torch.zeros((16, 2), dtype=torch.int32)
+    t.n_internal, t.n_free, t.grad, t._leaves = 1, 0, None, None
+
+    def query_packed(points):
+        o = OO.N3Tree(N=2, data_dim=49, depth_limit=L, radius=radius, center=center, data_format="SH16")
+        o.child, o.n_internal = t.child.numpy(), t.n_internal
+        node, ijk, _, _ = o.query(points.numpy())
+        return torch.from_numpy(o.pack_index(node, ijk))
+    t.query_packed = query_packed
+    g = torch.from_numpy(grid)
+    for _ in range(L - 1):
+        t[g].refine()
+    for j in range(0, g.shape[0], 700):
+        t[g[j:j + 700]].refine()
+    n = otree.n_internal
+    assert t.n_internal == n and t.max_depth == L and t.capacity >= n
+    assert (t.child[:n].numpy() == otree.child[:n]).all()
+    assert (t.parent_depth[:n].numpy() == otree.parent_depth[:n]).all()
+    lv = otree.leaves()
+    assert (t._all_leaves().numpy() == lv).all() and (t.depths.numpy() == otree.leaf_depths(lv)).all()
+    sel = np.nonzero(otree.leaf_depths(lv) == L)[0][:200]
+    u = rs.rand(sel.size, 3, 3).astype(np.float32)
+    got = t[torch.from_numpy(sel)].sample(3, torch.from_numpy(u)).numpy()
+    np.testing.assert_allclose(got, otree.sample(lv[sel], 3, u), rtol=0, atol=1e-6)
+    vals = torch.randn(sel.size, 49)
+    t[torch.from_numpy(sel)] = vals
+    t[:, -1:].relu_()
+    flat = t.data.reshape(-1, 49)
+    pk = otree.pack_index(lv[sel, 0], lv[sel, 1:])
+    assert torch.equal(flat[pk][:, :-1], vals[:, :-1]) and torch.equal(flat[pk][:, -1], vals[:, -1].clamp(min=0))
+    assert float(flat[:, -1].min()) >= 0.0
+    t.save(str(tmp_path / "t.npz"), compress=False)
+    assert t.capacity == n                                 # shrink_to_fit
+    z = np.load(str(tmp_path / "t.npz"))
+    assert z["data"].dtype == np.float16 and int(z["n_internal"]) == n and str(z["data_format"]) == "SH16"
+    t2 = NT.N3Tree.load(str(tmp_path / "t.npz"), map_location="cpu")
+    assert t2.n_internal == n and t2.N == 2 and repr(t2.data_format) == "SH16"
+    assert (t2.child.numpy() == otree.child[:n]).all()
+    assert float((t2.data - t.data).abs().max()) <= 2e-3 * float(t.data.abs().max())
+    # a depth-limited tree refuses to refine further
+    assert t[g[:10]].refine() is False
