@@ -569,3 +569,19 @@ def test_n3tree_host_bookkeeping_on_cpu(tmp_path):
     assert float((t2.data - t.data).abs().max()) <= 2e-3 * float(t.data.abs().max())
     # a depth-limited tree refuses to refine further
     assert t[g[:10]].refine() is False
+
+
+def test_camera_records_match_the_c_struct():
+    """pob_camera is 16 floats: c2w[3][4] row-major, fx, fy, width, height (include/plenoctree_b200.h)."""
+    import ctypes
+    from plenoctree_b200 import _lib
+    from plenoctree_b200.octree.renderer import camera_array, make_camera
+    assert ctypes.sizeof(_lib.Camera) == 64 and ctypes.sizeof(_lib.OctreeOpts) == 16
+    c2w = look_at_pose(4)
+    cam = make_camera(c2w, 800, 600, 1111.0)
+    rec = np.frombuffer(bytes(cam), dtype=np.float32)
+    assert np.array_equal(rec[:12], c2w[:3, :4].reshape(-1)) and list(rec[12:]) == [1111.0, 1111.0, 800.0, 600.0]
+    arr = camera_array(np.stack([c2w, look_at_pose(5)]), 800, 600, 1111.0, device="cpu").numpy()
+    assert arr.shape == (2, 16) and np.array_equal(arr[0], rec)
+    with pytest.raises(ValueError):
+        make_camera(np.eye(3), 8, 8, 1.0)
