@@ -585,3 +585,42 @@ def test_camera_records_match_the_c_struct():
     assert arr.shape == (2, 16) and np.array_equal(arr[0], rec)
     with pytest.raises(ValueError):
         make_camera(np.eye(3), 8, 8, 1.0)
+
+
+def test_backward_first_pass_equals_g_dot_out():
+    """svox's trace_ray_backward spends a whole march computing accum = sum_j w_j (c_j . g) + T_end * bg * sum(g);
+    the CUDA kernels use g . rgb of the forward render instead.  The two are the same number."""
+    tree = make_tree(8, 3, "SH16", density=0.4)
+    o, d, v = random_rays(9, 64)
+    g = np.random.RandomState(2).normal(size=(64, 3)).astype(np.float32)
+    rgb = OO.volume_render(tree, o, d, v, step_size=1e-3)
+    # accumulate pass 1 exactly like the oracle's backward does
+    rgba = False
+    K = 16
+    oo, dd, ds, invd, tmin, tmax = OO._setup(tree.offset, tree.invradius, o, d)
+    basis = OO.sh_basis(K, v)
+    miss = (tmax < 0) | (tmin > tmax)
+    accum = np.zeros(64, dtype=np.float64)
+    light = np.ones(64, dtype=np.float32)
+    t = tmin.copy()
+    active = ~miss & (t < tmax)
+    while active.any():
+        a = np.nonzero(active)[0]
+        pos = (oo[a] + t[a][:, None] * dd[a]).astype(np.float32)
+        node, ijk, cube, rel = tree.query_unit(pos)
+        smin, smax = OO._dda_unit(rel, invd[a])
+        delta_t = (((smax - smin) / cube).astype(np.float32) + np.float32(1e-3)).astype(np.float32)
+        sigma = tree.data[node, ijk[:, 0], ijk[:, 1], ijk[:, 2], -1]
+        h = sigma > 0
+        if h.any():
+            ah = a[h]
+            att = np.exp(-delta_t[h] * ds[ah] * sigma[h]).astype(np.float32)
+            w = light[ah] * (1 - att)
+            pre, _ = OO._leaf_color_pre(tree, basis[ah], node[h], ijk[h], K, rgba)
+            accum[ah] += w * (OO._sigmoid(pre) * g[ah]).sum(axis=1)
+            light[ah] *= att
+        t[a] = (t[a] + delta_t).astype(np.float32)
+        active = active & (t < tmax)
+    accum[~miss] += light[~miss] * 1.0 * g[~miss].sum(axis=1)
+    want = (g[~miss].astype(np.float64) * rgb[~miss]).sum(axis=1)
+    assert np.abs(accum[~miss] - want).max() < 1e-5
