@@ -113,7 +113,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import nerf_sh_oracle as O
-    from plenoctree_b200.nerf.utils import random_rays_np
+    from plenoctree_b200.nerf.rays import random_rays_np   # numpy only: the CPU arm maps no repo .so
     ref_rays = 256
     nsp = max(1, NSP * ref_rays // RAYS)
     torch.set_num_threads(min(os.cpu_count() or 1, 32))   # beyond ~32 threads torch-CPU gets slower here
@@ -159,7 +159,7 @@ def run_reference(args):
 
 def cpu_baseline_sample():
     from oracle import nerf_sh_oracle as O
-    from plenoctree_b200.nerf.utils import random_rays_np
+    from plenoctree_b200.nerf.rays import random_rays_np   # numpy only: the CPU arm maps no repo .so
     ref_rays = 256
     nsp = max(1, NSP * ref_rays // RAYS)
     torch.set_num_threads(min(os.cpu_count() or 1, 32))

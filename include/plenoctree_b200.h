@@ -169,11 +169,6 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
                       const float* sp_points_dev, float* grad_flat_dev, float* stats_dev, void* workspace_dev,
                       void* stream);
 
-/* Profiling aid for the opt-in fused backward (POB_FUSED_BWD=1): copies the per-CTA cycle counters of the last
- * pob_loss_and_grad call to out_host[3 launches][256 CTAs][4]  (producers: {spin tile X, spin tile Y, total X,
- * total Y}; consumers: {waiting for producers, waiting for a free stage, total, role}). */
-int pob_debug_bwdw_stalls(const pob_render_config* cfg, void* workspace_dev, unsigned long long* out_host);
-
 /* flax.optim.Adam (beta1 .9, beta2 .999, eps 1e-8; nerf_sh/nerf/models.py:44) on the flat buffers of
  * num_mlps MLPs, g = grad*grad_mult + weight_decay_coef*param, then re-packs the operand blobs.
  * `step` = number of updates already applied (flax optimizer.state.step). */
@@ -188,6 +183,14 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
 int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,
                         float* raw_sigma_dev, unsigned long long* trace_dev, int debug_flags, void* save_h_dev,
                         void* save_e_dev, void* save_mask_dev, void* stream);
+
+/* Profiling aid: one mlp_bwd launch (dgrad chain, FP16) on caller-provided inputs — per-sample gradients g_dev
+ * [m,4], view directions [m,3], relu masks (4 KB per 128 samples and layer), dZ / dO destinations sized like the
+ * training workspace — recording clock64() stamps of CTA 0 into trace_dev[2][256] (role 0 = MMA issuer, 1 = first
+ * epilogue warp of tile X); scripts/trace_summary.py.  debug_flags: timing experiments (results invalid). */
+int pob_debug_trace_bwd(const void* packed_dev, int sh_deg, int64_t m, const float* g_dev, const float* viewdirs_dev,
+                        const void* mask_dev, void* save_dz_dev, void* save_do_dev, unsigned long long* trace_dev,
+                        int debug_flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PlenOctree side.  These entry points stand where the

@@ -135,7 +135,7 @@ pob::FwdParams pob_base_params(const void* packed, int sh_deg) { return base_par
 
 extern "C" {
 
-int pob_abi_version(void) { return 2; }   // 2: pob_render_config grew sigma_noise_*_dev; octree entry points
+int pob_abi_version(void) { return 3; }   // 3: CTA-pair kernels (tile arrays padded to 4 tiles), pob_debug_bwdw_stalls removed
 
 long long pob_launch_count(void) { return g_launches.load(); }
 
@@ -220,6 +220,32 @@ int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_
   p.save_e = static_cast<uint8_t*>(save_e_dev);
   p.save_mask = static_cast<uint32_t*>(save_mask_dev);
   POB_CUDA("pob_debug_trace_fwd", pob::launch_mlp_fwd(p, 1, false, sm_count(), (cudaStream_t)stream));
+  return 0;
+}
+
+int pob_debug_trace_bwd(const void* packed_dev, int sh_deg, int64_t m, const float* g_dev, const float* viewdirs_dev,
+                        const void* mask_dev, void* save_dz_dev, void* save_do_dev, unsigned long long* trace_dev,
+                        int debug_flags, void* stream) {
+  if (int e = check_common("pob_debug_trace_bwd", packed_dev, sh_deg, POB_PREC_FP16)) return e;
+  if (!g_dev || !viewdirs_dev || !mask_dev || !save_dz_dev || !save_do_dev || m <= 0)
+    return fail("pob_debug_trace_bwd", "bad arguments");
+  pob::FwdParams base = base_params(packed_dev, sh_deg);
+  pob::BwdParams b;
+  memset(&b, 0, sizeof(b));
+  b.M = m;
+  b.G = reinterpret_cast<const float4*>(g_dev);
+  b.viewdirs = viewdirs_dev;
+  b.n_per_ray = 0;
+  b.w = base.w;
+  b.sh_deg = sh_deg;
+  b.K = base.K;
+  b.NH = base.NH;
+  b.mask = static_cast<const uint32_t*>(mask_dev);
+  b.save_dz = static_cast<uint8_t*>(save_dz_dev);
+  b.save_do = static_cast<uint8_t*>(save_do_dev);
+  b.trace = trace_dev;
+  b.debug_flags = debug_flags;
+  POB_CUDA("pob_debug_trace_bwd", pob::launch_mlp_bwd(b, sm_count(), (cudaStream_t)stream));
   return 0;
 }
 

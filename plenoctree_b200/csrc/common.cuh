@@ -29,6 +29,9 @@ constexpr int WSLOT_K       = 32;                  // K extent of one streamed w
 constexpr int WSLOT_BYTES   = WIDTH * WSLOT_K * 2; // [256 x 32] fp16, SW64 = 16 KB
 constexpr int NUM_WSLOTS    = 4;                   // weight ring depth
 constexpr int MAX_NH        = 80;                  // padded heads width (1 + 3*25 -> 80)
+// Rows of every per-sample training array (tile images, relu masks): samples are scheduled in units of four
+// 128-row tiles (one CTA pair x two tiles), so arrays are padded to a multiple of 512 rows.
+__host__ __device__ constexpr long long padded_rows(long long M) { return ((M + 511) / 512) * 512; }
 
 // Number of 32-wide K slots each forward layer streams (trunk 0..7, heads = index 8).
 // Biases ride on the tensor cores: column 63 of the posenc tile is the constant 1, so for layers 0 and
@@ -106,22 +109,6 @@ __device__ __forceinline__ void tc_fence_before() {
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-
-// ----------------------------------------------------------------------------------
-// Inter-CTA flags in global memory (producer/consumer queues of the fused backward kernel)
-// ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// generic-proxy writes (by any SM, made visible by an acquire) -> async-proxy (bulk copy) reads
-__device__ __forceinline__ void fence_proxy_async_all() {
-  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ----------------------------------------------------------------------------------
@@ -235,6 +222,19 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// Remote arrive with the default (release, cta-scope) semantics, as CUTLASS' ClusterBarrier::arrive does.  The
+// cluster-scope release costs ~1200 cycles per arrive (measured: it drains every outstanding store of the warp and
+// invalidates L1); the data handed over here lives in the arriving CTA's own shared memory and has already been
+// fenced for the async proxy (fence.proxy.async), so cta scope is what the hand-over needs.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// arrive on a barrier of this CTA (remote = false, shared::cta address) or of another CTA of the cluster
+// (remote = true, address from mapa_cluster)
+__device__ __forceinline__ void mbar_arrive_cluster_any(uint32_t addr, bool remote) {
+  if (remote) mbar_arrive_remote(addr);
+  else mbar_arrive(addr);
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;

@@ -49,7 +49,8 @@ struct FwdParams {
   uint32_t* save_mask;         // [8][ntile*128][8] relu masks (bit i of word c = col 32c+i)
   // ---- optional cycle trace of CTA 0 (debug/profiling; null = off): [3 roles][256] clock64 stamps
   unsigned long long* trace;
-  int debug_flags;             // timing experiments only (results invalid): 1 skip STS, 2 skip cvt/add, 4 skip LDTM
+  int debug_flags;             // timing experiments only (results invalid; pob_debug_trace_fwd): 8 no weight loads,
+                               // 16 h stores to one L2-resident tile per CTA, 32 drop in-epilogue stores, 64 drop deferred stores
 };
 
 // padded heads width for K spherical-harmonic coefficients per channel
@@ -63,6 +64,8 @@ inline size_t bwd_image_bytes(int NH) { return size_t((NH + 31) / 32 + 7 * 8) * 
 //            3 = error-compensated 3-pass split (hi*hi + lo*hi + hi*lo)
 cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int num_sms,
                            cudaStream_t stream);
+// single-pass forward / dgrad kernels run as CTA pairs (cta_group::2) unless POB_PAIR=0
+bool pair_mode_enabled();
 
 // flat fp32 parameters of one MLP in reference order (Dense_0..Dense_9: kernel [in,out] then
 // bias) -> packed images.  `nparams` = param_count(K).
@@ -95,21 +98,6 @@ cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const floa
 cudaError_t launch_sparsity_grad(const float* sigma_raw, int n, float length, float coef, float4* G,
                                  float* exp_sum, cudaStream_t st);
 
-// ---- producer/consumer queues of the fused dgrad+wgrad kernel (mlp_bwdw.cu) -------------------
-// Producer CTA p hands every dZ_l / dO tile pair of its current iteration to the layer-owning consumer
-// CTAs through a per-(producer, layer) double slot in global memory that is rewritten every iteration
-// (so it stays L2 resident) instead of a [ntile][8] array in HBM.
-constexpr int BWDW_QUEUES = 9;          // 0 = dO, 1 + (7 - l) = dZ_l  (order of production)
-struct BwdwQueues {
-  uint8_t* slots;           // [NP][9][2 tiles][64 KB]      (null = classic two-kernel path)
-  uint32_t* produced;       // [NP][9][2]   iterations written   (release/acquire, gpu scope)
-  uint32_t* consumed;       // [NP][9][2]   iterations consumed per reader (dZ_5 has two readers)
-  int NP;                   // number of producer CTAs = first consumer CTA
-  unsigned long long* stall; // optional [grid][4] cycle counters: spin time on flags / total (profiling)
-};
-inline size_t bwdw_slot_bytes(int NP) { return size_t(NP) * BWDW_QUEUES * 2 * 65536; }
-inline size_t bwdw_flag_count(int NP) { return size_t(NP) * BWDW_QUEUES * 2; }
-
 // ---- mlp_bwd.cu -----------------------------------------------------------------------------
 struct BwdParams {
   long long M;
@@ -121,7 +109,8 @@ struct BwdParams {
   const uint32_t* mask;     // [8][Mpad][8] from mlp_fwd
   uint8_t* save_dz;         // [ntile][8][64 KB]
   uint8_t* save_do;         // [ntile][32 KB]
-  BwdwQueues q;             // fused path: tiles go to the queues instead of save_dz / save_do
+  unsigned long long* trace;   // optional cycle trace of CTA 0 (null = off): [2 roles][256] clock64 stamps
+  int debug_flags;          // timing experiments only (results invalid): 1 no tile copy-out, 2 no mask loads
 };
 cudaError_t launch_mlp_bwd(const BwdParams& p, int num_sms, cudaStream_t stream);
 
@@ -138,17 +127,11 @@ struct WgradParams {
   int NH;
   float* partials;          // [num_ctas][WG_PARTIAL_FLOATS]
   short cta_role[WG_MAX_CTAS], cta_index[WG_MAX_CTAS], cta_count[WG_MAX_CTAS];
-  BwdwQueues q;             // fused path: A (or, for the heads, B) operand tiles come from the queues
-  long long num_iters;      // fused path: producer iterations (tile pairs) of the launch
 };
 // role -> [first CTA, count]; fills the per-CTA tables of `p`; returns number of CTAs to launch
 int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES],
                        int role_count[WG_NUM_ROLES]);
 cudaError_t launch_mlp_wgrad(const WgradParams& p, int num_ctas, cudaStream_t stream);
-// fused dgrad + wgrad: CTAs [0, q.NP) run the dgrad chain, CTAs [q.NP, q.NP + num_consumers) the wgrad roles
-// (cta_role/index/count are indexed by consumer number = blockIdx.x - q.NP)
-cudaError_t launch_mlp_bwdw(const BwdParams& b, const WgradParams& w, int num_consumers, cudaStream_t stream);
-int wgrad_assign_roles_n(WgradParams& p, int n, int role_start[WG_NUM_ROLES], int role_count[WG_NUM_ROLES]);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 // partials of one wgrad launch -> flat gradient of one MLP (reference layout), times inv_scale

@@ -19,15 +19,20 @@
 // 128x256 fp32 accumulators (512 columns).  NSPLIT = 3 evaluates ONE tile per iteration with
 // error-compensated fp16 operands (x = hi + lo; hi*hi + lo*hi + hi*lo), using the second tile's
 // buffers for the residual parts.
+//
+// PAIR (the default for NSPLIT = 1): two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 stream
+// over FOUR tiles (512 samples per iteration).  Every MMA has M = 256 (128 rows of tile X or Y from each CTA),
+// N = 256, and reads only HALF of the weight slot from each CTA's shared memory: per CTA and MMA the operand
+// fetch drops from 12 KB to 8 KB and the weight stream from 16 KB to 8 KB per slot.  That matters because the
+// shared-memory / L1 data pipe (128 B/clk) is what the single-CTA kernel saturates: operand fetch 96 B/clk +
+// weight fill 31 B/clk during the MMA phase, before the training variant adds its 128 KB of activation stores
+// per layer step (profiles/r2_*).  Only the leader CTA (cluster rank 0) issues MMAs; the
+// peer's warp 9 relays "my half-slot has landed" to the leader, the peer's epilogue warps arrive on the
+// leader's a_ready barriers through the cluster address map, and every commit is multicast to both CTAs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
-
-// Training saves: how many of the 8 32-column chunks of every h tile are stored only after the tile has been handed
-// to the MMA warp (0 = all from inside the epilogue: step 4.34 ms; 4: 4.26 ms; pacing the deferred stores with
-// __nanosleep made no difference — the stores and the weight stream share the L2 throughput cap).
-#ifndef POB_FWD_DEFER_CHUNKS
-#define POB_FWD_DEFER_CHUNKS 4
-#endif
 
 namespace pob {
 
@@ -47,9 +52,11 @@ constexpr uint32_t SM_W = SM_E1 + E_TILE_BYTES;
 constexpr uint32_t SM_TOTAL = SM_W + NUM_WSLOTS * WSLOT_BYTES;  // 229376
 static_assert(SM_TOTAL == 224 * 1024, "smem map");
 
+constexpr int MAX_RING = 8;   // pair mode: eight 8 KB half-slots in the same 64 KB
 struct Barriers {
-  uint64_t full[NUM_WSLOTS];
-  uint64_t empty[NUM_WSLOTS];
+  uint64_t full[MAX_RING];
+  uint64_t empty[MAX_RING];
+  uint64_t pfull[MAX_RING];   // pair mode, leader only: the peer's half of the slot has landed
   uint64_t a_ready[2];
   uint64_t d_ready[2];
 };
@@ -153,57 +160,79 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, ui
 // OUTM (= p.out_mode) is a template parameter so that each instantiation carries only its own heads
 // epilogue: the fully unrolled 80-column heads loop with all four output modes inlined made the kernel
 // 145+ KB of SASS and cost ~8 % of inference throughput in instruction-cache misses.
-template <int NSPLIT, int OUTM, bool SAVE>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
-mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+template <int NSPLIT, int OUTM, bool SAVE, bool PAIR>
+__device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
+  static_assert(!PAIR || NSPLIT == 1, "CTA pairs run the single-pass mode only");
   constexpr bool PRECISE = (NSPLIT == 3);
-  extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) Barriers bars;
   __shared__ uint32_t tmem_base_s;
 
-  constexpr int ROWS_PER_ITER = (NSPLIT == 1) ? 2 * TILE_M : TILE_M;
-  constexpr int NTILES = (NSPLIT == 1) ? 2 : 1;
+  constexpr int NTILES = (NSPLIT == 1) ? 2 : 1;                       // tiles per CTA and iteration
+  constexpr int TILES_PER_ITER = PAIR ? 4 : NTILES;                   // tiles per scheduling unit (CTA or pair)
+  constexpr int ROWS_PER_ITER = TILES_PER_ITER * TILE_M;
+  constexpr int RING = PAIR ? MAX_RING : NUM_WSLOTS;
+  constexpr uint32_t RSLOT_BYTES = PAIR ? WSLOT_BYTES / 2 : WSLOT_BYTES;
   const long long num_iters = (p.M + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t sbase = smem_u32(smem);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                // 0 = leader (issues the MMAs)
+  const long long unit = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long nunits = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NUM_WSLOTS; ++i) {
+    for (int i = 0; i < RING; ++i) {
       mbar_init(smem_u32(&bars.full[i]), 1);
       mbar_init(smem_u32(&bars.empty[i]), 1);
+      mbar_init(smem_u32(&bars.pfull[i]), 1);
     }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&bars.a_ready[g]), NSPLIT == 1 ? 4 : 8);
+      // one arrival per epilogue warp that writes the operand tile(s) the MMA reads: 4 (own tile), 8 in the
+      // x3 mode (both groups write one tile) and in pair mode (the peer's four warps arrive remotely)
+      mbar_init(smem_u32(&bars.a_ready[g]), (NSPLIT == 1 && !PAIR) ? 4 : 8);
       mbar_init(smem_u32(&bars.d_ready[g]), 1);
     }
     fence_mbar_init();
   }
-  if (warp == PRODUCER_WARP) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  if (warp == PRODUCER_WARP) {
+    if (PAIR) tmem_alloc_pair(smem_u32(&tmem_base_s), 512);
+    else tmem_alloc(smem_u32(&tmem_base_s), 512);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const int NH = p.NH;
+  auto wait_bar = [&](uint64_t* b, uint32_t parity) {
+    mbar_wait(smem_u32(b), parity);   // (arrivals may come from the other CTA; cta-scope acquire is enough)
+  };
 
   if (warp == PRODUCER_WARP) {
     // =============================== weight producer ===================================
+    // pair mode: this CTA streams rows [128 rank, +128) of every trunk slot (rows [NH/2 rank, +NH/2) of the
+    // heads slots) = the contiguous half `rank` of the slot image
     uint32_t slot = 0, phase = 0;
-    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+    for (long long it = unit; it < num_iters; it += nunits) {
       size_t off = 0;
       for (int l = 0; l <= NUM_TRUNK; ++l) {
         const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
         const uint32_t bytes = (l == NUM_TRUNK) ? uint32_t(NH) * 64u : uint32_t(WSLOT_BYTES);
+        const uint32_t cbytes = PAIR ? bytes / 2 : bytes;
         for (int j = 0; j < ns; ++j) {
 #pragma unroll
           for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); ++part) {
-            mbar_wait(smem_u32(&bars.empty[slot]), phase ^ 1);
+            wait_bar(&bars.empty[slot], phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(smem_u32(&bars.full[slot]), bytes);
-              bulk_g2s(sbase + SM_W + slot * WSLOT_BYTES, (part == 0 ? p.w.w_hi : p.w.w_lo) + off, bytes,
-                       smem_u32(&bars.full[slot]));
+              if (p.debug_flags & 8) {   // timing experiment: no weight traffic at all (results are garbage)
+                mbar_arrive(smem_u32(&bars.full[slot]));
+              } else {
+                mbar_arrive_expect_tx(smem_u32(&bars.full[slot]), cbytes);
+                bulk_g2s(sbase + SM_W + slot * RSLOT_BYTES, (part == 0 ? p.w.w_hi : p.w.w_lo) + off + rank * cbytes,
+                         cbytes, smem_u32(&bars.full[slot]));
+              }
             }
             __syncwarp();
-            if (++slot == NUM_WSLOTS) {
+            if (++slot == RING) {
               slot = 0;
               phase ^= 1;
             }
@@ -219,12 +248,30 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     // wrap every UTCHMMA in a divergence-handling ELECT loop and slows the issue rate below the
     // tensor pipe's 128 cycles per 128x256x16 MMA.)
     uint32_t slot = 0, phase = 0, aphase = 0, tn = 0;
-    const uint32_t idesc_t = make_idesc_f16(TILE_M, WIDTH);
-    const uint32_t idesc_h = make_idesc_f16(TILE_M, NH);
+    if (PAIR && rank != 0) {
+      // peer CTA: no MMAs to issue; relay every landed half-slot to the leader's pfull barrier
+      const uint32_t pfull0 = mapa_cluster(smem_u32(&bars.pfull[0]), 0);
+      for (long long it = unit; it < num_iters; it += nunits) {
+        for (int l = 0; l <= NUM_TRUNK; ++l) {
+          const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
+          for (int j = 0; j < ns; ++j) {
+            mbar_wait(smem_u32(&bars.full[slot]), phase);
+            if (lane == 0) mbar_arrive_remote(pfull0 + slot * 8u);
+            __syncwarp();
+            if (++slot == RING) {
+              slot = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else {
+    const uint32_t idesc_t = make_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, WIDTH);
+    const uint32_t idesc_h = make_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, NH);
     constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
     constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
     const uint32_t w_base = sbase + SM_W;
-    for (long long it = blockIdx.x; it < num_iters; it += gridDim.x) {
+    for (long long it = unit; it < num_iters; it += nunits) {
       for (int l = 0; l <= NUM_TRUNK; ++l) {
         const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
         const uint32_t idesc = (l == NUM_TRUNK) ? idesc_h : idesc_t;
@@ -239,13 +286,14 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
           const uint32_t s_hi = slot;
           const uint32_t s_lo = slot + 1;  // x3 only; ring depth is even: hi/lo never straddle the wrap
           mbar_wait(smem_u32(&bars.full[s_hi]), phase);
+          if (PAIR) mbar_wait(smem_u32(&bars.pfull[s_hi]), phase);   // the peer's half of the slot
           if (NSPLIT == 3) mbar_wait(smem_u32(&bars.full[s_lo]), phase);
-          const uint64_t bh0 = W_HI | uint64_t(((w_base + s_hi * WSLOT_BYTES) >> 4) & 0x3FFF);
-          const uint64_t bl0 = W_HI | uint64_t(((w_base + s_lo * WSLOT_BYTES) >> 4) & 0x3FFF);
+          const uint64_t bh0 = W_HI | uint64_t(((w_base + s_hi * RSLOT_BYTES) >> 4) & 0x3FFF);
+          const uint64_t bl0 = W_HI | uint64_t(((w_base + s_lo * RSLOT_BYTES) >> 4) & 0x3FFF);
 #pragma unroll
           for (int g = 0; g < NTILES; ++g) {
             if (j == 0) {
-              mbar_wait(smem_u32(&bars.a_ready[g]), aphase);   // tile g's operand tile written, D drained
+              wait_bar(&bars.a_ready[g], aphase);   // tile g's operand tile(s) written, D drained (both CTAs)
               if (g == 0) trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);
             }
             tc_fence_after();
@@ -253,7 +301,11 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
               const uint32_t a_base = sbase + (from_e ? (g ? SM_E1 : SM_E0) : (g ? SM_A1 : SM_A0)) + a_off;
               const uint64_t ah0 = A_HI | uint64_t((a_base >> 4) & 0x3FFF);
               const uint32_t d = tmem + uint32_t(g) * 256u;
-              if (NSPLIT == 1) {
+              if (PAIR) {
+                // M = 256: rows 0-127 = this CTA's tile g, rows 128-255 = the peer's tile g (same offsets)
+                if (!bias_slot) umma_f16_pair(d, ah0, bh0, idesc, j != 0);
+                umma_f16_pair(d, ah0 + 2, bh0 + 2, idesc, 1u);
+              } else if (NSPLIT == 1) {
                 if (!bias_slot) umma_f16(d, ah0, bh0, idesc, j != 0);
                 umma_f16(d, ah0 + 2, bh0 + 2, idesc, 1u);      // k16 step 1: +32 bytes = +2 encoded
               } else {
@@ -269,17 +321,22 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
                 umma_f16(d, ah0 + 2, bl0 + 2, idesc, 1u);
                 umma_f16(d, ah0 + 2, bh0 + 2, idesc, 1u);
               }
-              if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
-              if (g == NTILES - 1) {
-                umma_commit(smem_u32(&bars.empty[s_hi]));
-                if (NSPLIT == 3) umma_commit(smem_u32(&bars.empty[s_lo]));
+              if (PAIR) {
+                if (j == ns - 1) umma_commit_pair(smem_u32(&bars.d_ready[g]), 0x3);
+                if (g == NTILES - 1) umma_commit_pair(smem_u32(&bars.empty[s_hi]), 0x3);
+              } else {
+                if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
+                if (g == NTILES - 1) {
+                  umma_commit(smem_u32(&bars.empty[s_hi]));
+                  if (NSPLIT == 3) umma_commit(smem_u32(&bars.empty[s_lo]));
+                }
               }
             }
             __syncwarp();
           }
           __syncwarp();
           slot += (NSPLIT == 3) ? 2 : 1;
-          if (slot == NUM_WSLOTS) {
+          if (slot == RING) {
             slot = 0;
             phase ^= 1;
           }
@@ -288,11 +345,12 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
         trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);       // all MMAs of the layer issued
       }
     }
+    }
   } else {
     // ================================ epilogue warps ====================================
     const int g = warp >> 2;                       // group
     const int row = int((warp & 3) * 32 + lane);   // TMEM lane == tile row
-    const int tile_in_iter = (NSPLIT == 1) ? g : 0;
+    const int tile_in_iter = (NSPLIT == 1) ? int(rank) * 2 + g : 0;   // pair: leader owns tiles 0,1, peer 2,3
     const int bar_id = (NSPLIT == 1) ? g : 0;
     // column range of the trunk epilogue handled by this thread, in 32-column chunks
     const int c_begin = (NSPLIT == 1) ? 0 : 4 * g;
@@ -302,46 +360,44 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     uint8_t* const e_hi = smem + ((NSPLIT == 1 && g == 1) ? SM_E1 : SM_E0);
     uint8_t* const e_lo = smem + SM_E1;
     const int unit_lo = (NSPLIT == 1) ? 0 : 4 * g, unit_hi = (NSPLIT == 1) ? 8 : 4 * g + 4;
-    const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(tile_in_iter) * 256u;
+    const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(bar_id) * 256u;
     constexpr bool saving = SAVE;   // training launches (NSPLIT == 1): store h_l tiles, posenc tiles and relu masks
     uint32_t dphase = 0, tn = 0;
     const bool tracer = (warp & 3) == 0 && lane == 0;
     unsigned long long* const trp = tracer ? p.trace : nullptr;
     const int trole = 1 + g;
 
+    // the MMA issuer (leader CTA) waits on ITS a_ready barrier: the peer's warps arrive through the cluster map
+    const uint32_t a_ready_addr = (PAIR && rank != 0) ? mapa_cluster(smem_u32(&bars.a_ready[bar_id]), 0)
+                                                      : smem_u32(&bars.a_ready[bar_id]);
     auto signal_a_ready = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars.a_ready[bar_id]));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster_any(a_ready_addr, rank != 0);
+        else mbar_arrive(a_ready_addr);
+      }
     };
 
-    long long it = blockIdx.x;
+    long long it = unit;
     if (it < num_iters) {
       float x, y, z;
       load_point(p, it * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
       posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi,
-                                  saving ? p.save_e + size_t(it * NTILES + tile_in_iter) * E_TILE_BYTES : nullptr);
+                                  saving ? p.save_e + size_t(it * TILES_PER_ITER + tile_in_iter) * E_TILE_BYTES : nullptr);
       signal_a_ready();
     }
-    for (; it < num_iters; it += gridDim.x) {
-      const long long tile_idx = it * NTILES + tile_in_iter;
+    for (; it < num_iters; it += nunits) {
+      const long long tile_idx = it * TILES_PER_ITER + tile_in_iter;
       const long long s = tile_idx * TILE_M + row;
       // ------------------------------ trunk layers ------------------------------------
       for (int l = 0; l < NUM_TRUNK; ++l) {
-        mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
+        wait_bar(&bars.d_ready[bar_id], dphase);
         dphase ^= 1;
         tc_fence_after();
         trace_stamp(trp, trole, tn);             // d_ready observed
-        // training: h_l tiles go to global memory straight from the epilogue registers, in the "T" layout
-        // (layouts.py: t_tile_offset) that mlp_wgrad reads MN-major without swizzle.  Copying the tile out of
-        // shared memory instead (bulk store, or LDS + STG) competes with the next layer's MMA operand reads:
-        // the SS-mode MMA alone needs 96 of the 128 B/clk of shared-memory bandwidth.
-        uint8_t* const h_glob = saving ? p.save_h + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES : nullptr;
-        uint32_t maskw[8];
         constexpr int NCH = (NSPLIT == 1) ? 8 : 4;
-        constexpr int DEFER_CH = (SAVE && NSPLIT == 1) ? POB_FWD_DEFER_CHUNKS : 0;
-        uint32_t defer[DEFER_CH > 0 ? DEFER_CH * 16 : 1];
         uint32_t va[32], vb[32];
         tmem_ld32(d_tmem + c_begin * 32, va);
 #pragma unroll
@@ -350,7 +406,6 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
           uint32_t(&v)[32] = (cc & 1) ? vb : va;
           tmem_ld_wait();                                    // chunk cc has landed
           if (cc + 1 < NCH) tmem_ld32(d_tmem + (c + 1) * 32, (cc & 1) ? va : vb);   // prefetch chunk cc+1
-          uint32_t mbits = 0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             // bias already accumulated by the tensor cores: ReLU + fp16 pack is all that is left
@@ -358,28 +413,10 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               w[i] = pack_f16x2_relu(__uint_as_float(v[8 * u + 2 * i]), __uint_as_float(v[8 * u + 2 * i + 1]));
-            if (NSPLIT == 1 && saving) {
-              // relu mask: shift the sign bit of each pre-activation into mbits (inverted once per word
-              // below); column 32c+i ends up at bit (31-i)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) mbits = __funnelshift_l(v[8 * u + i], mbits, 1);
-            }
             const uint32_t unit = uint32_t((c & 1) * 4 + u);
             const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
                                  ((unit ^ uint32_t(row & 7)) << 4);
             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (saving) {   // T layout: [32-row group][8-column unit][row][16 B] -> 512 contiguous bytes per warp store
-              if (cc < NCH - DEFER_CH) {
-                *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
-                    make_uint4(w[0], w[1], w[2], w[3]);
-              } else {
-                // the last DEFER_CH chunks wait in registers and are stored after the tile has been handed to the
-                // MMA warp: the store stream then overlaps the next layer's MMAs (HBM otherwise idles through
-                // every MMA phase, because a write-back L2 drains only when new stores push it)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) defer[(cc - (NCH - DEFER_CH)) * 16 + u * 4 + i] = w[i];
-              }
-            }
             if (NSPLIT == 3) {
               uint32_t wl[4];
 #pragma unroll
@@ -391,48 +428,68 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
               *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
             }
           }
-          maskw[cc] = ~mbits;
           if (cc == 0) trace_stamp(trp, trole, tn);   // first chunk done
         }
         trace_stamp(trp, trole, tn);             // accumulator drained, A tile written
-        if (saving) {
-          if (NSPLIT == 1) {
-            const long long mrows = ((p.M + 2 * TILE_M - 1) / (2 * TILE_M)) * (2 * TILE_M);
-            uint4* mp = reinterpret_cast<uint4*>(p.save_mask + (size_t(l) * mrows + s) * 8);
-            mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
-            mp[1] = make_uint4(maskw[NCH - 4], maskw[NCH - 3], maskw[NCH - 2], maskw[NCH - 1]);
-          }
-        }
         signal_a_ready();
         trace_stamp(trp, trole, tn);             // a_ready signalled
-        if (saving && DEFER_CH > 0) {
+        if (saving && NSPLIT == 1) {
+          // Training saves, AFTER the hand-over (off the MMA -> epilogue -> MMA critical path): every thread reads its
+          // own row of the finished tile back from shared memory (the next layer's MMAs only read it too), stores it
+          // to global memory in the "T" layout (layouts.py: t_tile_offset; 512 contiguous bytes per warp store) that
+          // mlp_wgrad contracts MN-major without swizzle, and derives the ReLU mask of the row from the fp16 values
+          // (h > 0 <=> fp16(h) != 0 up to fp16 underflow).  Mask word c covers columns 32c..32c+31: column 32c+2k is
+          // bit 15-k, column 32c+2k+1 is bit 31-k (two instructions per fp16 pair; mlp_bwd tests the same bits).
+          // The store stream (64 KB per tile and layer against ~25-30 B/clk of SM store bandwidth) is the longest
+          // stage of the training forward: it has the whole MMA phase to drain.  Measured alternatives
+          // (scripts/overlap_probe.cu, profiles/r2_overlap_probe.json): stores issued from inside the epilogue stall
+          // it, because a backed-up st.global queue blocks the warp's later st.shared / fences; a TMA bulk store of the
+          // tile collides with the weight-slot TMA loads (258 vs 170 cycles per MMA).
+          // debug flag 16 (timing experiment): every h store lands in one 64 KB scratch tile per CTA (L2, not HBM)
+          uint8_t* const h_glob = p.save_h + ((p.debug_flags & 16) ? size_t(blockIdx.x)
+                                                                   : (size_t(tile_idx) * NUM_TRUNK + l)) * A_TILE_BYTES;
+          uint32_t maskw[8];
 #pragma unroll
-          for (int dc = 0; dc < DEFER_CH; ++dc) {
-            const int c = c_begin + NCH - DEFER_CH + dc;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t mbits = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) =
-                  make_uint4(defer[dc * 16 + u * 4], defer[dc * 16 + u * 4 + 1], defer[dc * 16 + u * 4 + 2],
-                             defer[dc * 16 + u * 4 + 3]);
+              const uint32_t unit = uint32_t((c & 1) * 4 + u);
+              const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
+                                   ((unit ^ uint32_t(row & 7)) << 4);
+              uint4 q = make_uint4(off, row, c, u);
+              if (!(p.debug_flags & 256)) q = *reinterpret_cast<const uint4*>(a_hi + off);   // 256: no LDS
+              if (!(p.debug_flags & 64))   // 64: timing experiment, no h stores at all
+                *reinterpret_cast<uint4*>(h_glob + uint32_t(warp & 3) * 16384u + uint32_t(c * 4 + u) * 512u + lane * 16u) = q;
+              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+              if (p.debug_flags & 128) { mbits ^= q.x; continue; }   // 128: no mask arithmetic
+#pragma unroll
+              for (int i = 0; i < 4; ++i)   // non-negative fp16 pair -> 0/1 per half (VIMNMX.U16x2), shifted in
+                mbits = (mbits << 1) + __vminu2(qw[i], 0x00010001u);
             }
+            maskw[c] = mbits;
           }
+          const long long mrows = padded_rows(p.M);
+          uint4* mp = reinterpret_cast<uint4*>(p.save_mask + (size_t(l) * mrows + s) * 8);
+          mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
+          mp[1] = make_uint4(maskw[4], maskw[5], maskw[6], maskw[7]);
         }
         if (l == SKIP_LAYER) {
           // E is dead until the next iteration: encode the next tile now, in the shadow of the
           // layer-6/7/heads MMAs.
-          const long long nit = it + gridDim.x;
+          const long long nit = it + nunits;
           if (nit < num_iters) {
             float x, y, z;
             load_point(p, nit * ROWS_PER_ITER + tile_in_iter * TILE_M + row, x, y, z);
             posenc_row<NSPLIT, PRECISE>(e_hi, e_lo, row, x, y, z, unit_lo, unit_hi,
-                                        saving ? p.save_e + size_t(nit * NTILES + tile_in_iter) * E_TILE_BYTES
+                                        saving ? p.save_e + size_t(nit * TILES_PER_ITER + tile_in_iter) * E_TILE_BYTES
                                                : nullptr);
             fence_proxy_async_smem();
           }
         }
       }
       // -------------------------------- heads ------------------------------------------
-      mbar_wait(smem_u32(&bars.d_ready[bar_id]), dphase);
+      wait_bar(&bars.d_ready[bar_id], dphase);
       dphase ^= 1;
       tc_fence_after();
       if (NSPLIT == 1 || g == 0) {
@@ -536,17 +593,50 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == PRODUCER_WARP) tmem_dealloc(tmem, 512);
+  if (PAIR) {
+    // every epilogue warp has seen the last d_ready = every MMA that reads either CTA's shared memory is done
+    cluster_sync_all();
+    if (warp == PRODUCER_WARP) tmem_dealloc_pair(tmem, 512);
+  } else {
+    __syncthreads();
+    if (warp == PRODUCER_WARP) tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int NSPLIT, int OUTM, bool SAVE>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  fwd_body<NSPLIT, OUTM, SAVE, false>(p, smem);
+}
+
+template <int OUTM, bool SAVE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
+mlp_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  fwd_body<1, OUTM, SAVE, true>(p, smem);
+}
+
+// POB_PAIR=0 selects the single-CTA kernels for the single-pass mode (A/B experiments; default: CTA pairs)
+bool pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POB_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
 }
 
 cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int num_sms,
                            cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
-  const int rows = (nsplit == 1) ? 2 * TILE_M : TILE_M;
-  long long iters = (p.M + rows - 1) / rows;
-  int grid = int(iters < num_sms ? iters : num_sms);
   (void)precise_sin;   // tied to the precision mode: FP16X3 uses libdevice sinf, FP16 the reduced SFU sine
+  if (nsplit != 1 && nsplit != 3) return cudaErrorInvalidValue;
+  const bool pair = nsplit == 1 && num_sms >= 2 && pair_mode_enabled();
+  const int rows = pair ? 4 * TILE_M : ((nsplit == 1) ? 2 * TILE_M : TILE_M);
+  const long long iters = (p.M + rows - 1) / rows;
+  const int units = pair ? num_sms / 2 : num_sms;
+  const int grid = int(iters < units ? iters : units) * (pair ? 2 : 1);
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e =
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
@@ -554,11 +644,19 @@ cudaError_t launch_mlp_fwd(const FwdParams& p, int nsplit, bool precise_sin, int
     kernel<<<grid, FWD_THREADS, SM_TOTAL, stream>>>(p);
     return cudaGetLastError();
   };
-  if (nsplit != 1 && nsplit != 3) return cudaErrorInvalidValue;
   const bool save = p.save_h != nullptr;
   if (save && (nsplit != 1 || !p.save_e || !p.save_mask ||
                (p.out_mode != OUT_RGBS && p.out_mode != OUT_SIGMA)))
     return cudaErrorInvalidValue;
+  if (pair) {
+    switch (p.out_mode) {
+      case OUT_RAW: return launch(mlp_fwd_pair_kernel<OUT_RAW, false>);
+      case OUT_SIGMA: return save ? launch(mlp_fwd_pair_kernel<OUT_SIGMA, true>) : launch(mlp_fwd_pair_kernel<OUT_SIGMA, false>);
+      case OUT_RGBS: return save ? launch(mlp_fwd_pair_kernel<OUT_RGBS, true>) : launch(mlp_fwd_pair_kernel<OUT_RGBS, false>);
+      case OUT_CELL_MEAN: return launch(mlp_fwd_pair_kernel<OUT_CELL_MEAN, false>);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (p.out_mode) {
     case OUT_RAW:
       return nsplit == 1 ? launch(mlp_fwd_kernel<1, OUT_RAW, false>) : launch(mlp_fwd_kernel<3, OUT_RAW, false>);

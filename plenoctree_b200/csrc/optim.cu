@@ -8,13 +8,8 @@ namespace pob {
 
 // Work split of the wgrad launch.  The kernel is bound by the tile bytes each role streams
 // (128 KB per tile for the 256x256 layers, ~80-96 KB for Dense_0 / the skip rows / the heads).
-int wgrad_assign_roles(WgradParams& p, int num_sms, int role_start[WG_NUM_ROLES],
+int wgrad_assign_roles(WgradParams& p, int n_in, int role_start[WG_NUM_ROLES],
                        int role_count[WG_NUM_ROLES]) {
-  return wgrad_assign_roles_n(p, num_sms, role_start, role_count);
-}
-
-int wgrad_assign_roles_n(WgradParams& p, int n_in, int role_start[WG_NUM_ROLES],
-                         int role_count[WG_NUM_ROLES]) {
   int n = n_in < WG_MAX_CTAS ? n_in : WG_MAX_CTAS;
   if (n < WG_NUM_ROLES) n = WG_NUM_ROLES;  // one CTA per role at the very least (they time-share SMs)
   int small = (n * 8) / 100;               // per small role

@@ -34,42 +34,14 @@ struct Level {
 
 struct Workspace {
   Level lv[3];        // coarse, fine, sparsity
-  float* partials[3]; // wgrad partials of the coarse / fine / sparsity launches
-  uint8_t* q_slots;   // fused backward: producer->consumer tile queues (L2 resident)
-  uint32_t* q_flags;  // produced[NP*9*2] then consumed[NP*9*2]
-  unsigned long long* q_stall;   // [3 jobs][160+][4] profiling counters of the fused backward
+  float* partials[2]; // wgrad partials of the two MLPs' launches
   size_t total;
 };
 
-#include <cstdlib>
-// Fused backward (dgrad producers + wgrad consumers in one launch, dZ tiles through L2-resident queues).
-// Correct (same parity tests) but, as of round 1, slower than the two-kernel path (3.1 vs 2.7 ms per step:
-// with ~80 of 148 SMs producing, the serialized MMA / epilogue / copy-out phases of a producer bound the
-// launch), so it is opt-in: POB_FUSED_BWD=1, producer count POB_BWDW_NP.
-bool fused_bwd_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("POB_FUSED_BWD");
-    v = e ? atoi(e) : 0;
-  }
-  return v != 0;
-}
-int fused_bwd_producers(int sms) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("POB_BWDW_NP");
-    v = e ? atoi(e) : 0;
-  }
-  int np = v > 0 ? v : (sms * 59 + 50) / 100;   // dgrad : wgrad work ~ 0.59 : 0.41 (measured cycle counts)
-  if (np > sms - WG_NUM_ROLES) np = sms - WG_NUM_ROLES;
-  if (np < 1) np = 1;
-  return np;
-}
-constexpr int MAX_PRODUCERS = 160;
-
 size_t up(size_t x) { return (x + 1023) / 1024 * 1024; }
 
-long long tiles_for(long long M) { return ((M + 255) / 256) * 2; }
+// tiles are scheduled four at a time (one CTA pair x two tiles): every per-tile array is padded to that unit
+long long tiles_for(long long M) { return padded_rows(M) / TILE_M; }
 
 // deterministic carve of the caller-provided workspace
 Workspace carve(const pob_render_config& c, int training, uint8_t* base) {
@@ -109,10 +81,7 @@ Workspace carve(const pob_render_config& c, int training, uint8_t* base) {
     }
   }
   if (training) {
-    for (int i = 0; i < 3; ++i) w.partials[i] = (float*)take(sizeof(float) * WG_MAX_CTAS * WG_PARTIAL_FLOATS);
-    w.q_slots = take(bwdw_slot_bytes(MAX_PRODUCERS));
-    w.q_flags = (uint32_t*)take(2 * bwdw_flag_count(MAX_PRODUCERS) * sizeof(uint32_t));
-    w.q_stall = (unsigned long long*)take(3 * 256 * 4 * sizeof(unsigned long long));
+    for (int i = 0; i < 2; ++i) w.partials[i] = (float*)take(sizeof(float) * WG_MAX_CTAS * WG_PARTIAL_FLOATS);
   }
   w.total = off;
   return w;
@@ -324,50 +293,7 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
   if (Nf > 0) jobs[njobs++] = Job{packed_fine_dev, &F, (long long)n_rays * (Nc + Nf), viewdirs_dev, Nc + Nf, 1};
   if (sparsity) jobs[njobs++] = Job{pk_main, &S, sp_n, sp_points_dev, 0, Nf > 0 ? 1 : 0};
 
-  if (fused_bwd_enabled() && sms >= 2 * WG_NUM_ROLES) {
-    // One persistent launch per level: dgrad producers + layer-owning wgrad consumers, dZ tiles through
-    // L2-resident queues.  Partials of the launches that feed the same MLP are summed by reduce_grads.
-    const int NP = fused_bwd_producers(sms);
-    const int NC = sms - NP;
-    int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];
-    const float* part_of_mlp[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    for (int j = 0; j < njobs; ++j) {
-      Job& J = jobs[j];
-      BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
-      b.q.slots = w.q_slots;
-      b.q.produced = w.q_flags;
-      b.q.consumed = w.q_flags + bwdw_flag_count(MAX_PRODUCERS);
-      b.q.NP = NP;
-      b.q.stall = w.q_stall + size_t(j) * 256 * 4;
-      WgradParams g;
-      memset(&g, 0, sizeof(g));
-      g.seg[0] = WgradSegment{J.L->H, J.L->DZ, J.L->E, J.L->DO};
-      g.seg_tiles[0] = tiles_for(J.M);
-      g.NH = NH;
-      g.partials = w.partials[j];
-      g.q = b.q;
-      g.num_iters = (J.M + 2 * TILE_M - 1) / (2 * TILE_M);
-      wgrad_assign_roles_n(g, NC, rs, rc);
-      POB_CUDA(where, cudaMemsetAsync(w.q_flags, 0, 2 * bwdw_flag_count(MAX_PRODUCERS) * sizeof(uint32_t), st));
-      {
-        pob_count_launch();
-        PobPhaseTimer _t(POB_PH_BWD, st);
-        POB_CUDA(where, launch_mlp_bwdw(b, g, NC, st));
-      }
-      const float** slot = part_of_mlp[J.mlp];
-      if (!slot[0]) slot[0] = w.partials[j];
-      else slot[1] = w.partials[j];
-    }
-    for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
-      pob_count_launch();
-      PobPhaseTimer _t(POB_PH_OPTIM, st);
-      POB_CUDA(where, launch_reduce_grads(part_of_mlp[mlp][0], rs, rc, K, 1.0f / hp->loss_scale,
-                                          grad_flat_dev + size_t(mlp) * P, st, part_of_mlp[mlp][1]));
-    }
-    return 0;
-  }
-
-  // ---- classic path: dgrad launches, then one wgrad launch per MLP over the saved dZ / h tiles ----
+  // ---- dgrad launches, then one wgrad launch per MLP over the saved dZ / h tiles ----
   for (int j = 0; j < njobs; ++j) {
     Job& J = jobs[j];
     BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
@@ -395,15 +321,6 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     { pob_count_launch(); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
                                         grad_flat_dev + size_t(mlp) * P, st)); }
   }
-  return 0;
-}
-
-int pob_debug_bwdw_stalls(const pob_render_config* cfg, void* workspace_dev, unsigned long long* out_host) {
-  if (check_cfg("pob_debug_bwdw_stalls", cfg)) return 1;
-  if (!workspace_dev || !out_host) return pob_fail("pob_debug_bwdw_stalls", "NULL pointer");
-  Workspace w = carve(*cfg, 1, (uint8_t*)workspace_dev);
-  POB_CUDA("pob_debug_bwdw_stalls", cudaMemcpy(out_host, w.q_stall, 3 * 256 * 4 * sizeof(unsigned long long),
-                                               cudaMemcpyDeviceToHost));
   return 0;
 }
 

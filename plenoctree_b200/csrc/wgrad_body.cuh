@@ -1,6 +1,5 @@
 #pragma once
-// wgrad_body.cuh — device body shared by mlp_wgrad.cu (classic) and mlp_bwdw.cu (fused).
-// mlp_wgrad.cu — weight-gradient contraction over samples (the wgrad half of jax.value_and_grad,
+// wgrad_body.cuh — device body of mlp_wgrad.cu: weight-gradient contraction over samples (the wgrad half of jax.value_and_grad,
 // nerf_sh/train.py:116):   dW_l[out, in] = sum_s dZ_l[s, out] * h_{l-1}[s, in],  db_l = sum_s dZ_l[s, :]
 //
 // A 256x256 fp32 accumulator is exactly one SM's tensor memory (2 x 128 lanes x 256 columns), so
@@ -72,18 +71,13 @@ __device__ __forceinline__ RoleInfo role_info(int role, int NH) {
 }  // namespace
 
 
-// One unit of consumer work = one 128-sample tile (two 64-sample stages).
+// One unit of work = one 128-sample tile (two 64-sample stages).
 struct WgItem {
   const uint8_t* a_ptr;
   const uint8_t* b_ptr;
-  const uint32_t* wait_flag;   // fused: produced counter of the queue slot, null otherwise
-  uint32_t wait_val;
-  uint32_t* done_flag;         // fused: consumed counter to publish after the pair's last stage landed
-  uint32_t done_val;
-  bool valid;
 };
 
-// cta = consumer index within the launch (indexes cta_role/index/count and the partials)
+// cta indexes cta_role/index/count and the partials
 __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, const int cta) {
   __shared__ __align__(8) WgBarriers bars;
   __shared__ uint32_t tmem_base_s;
@@ -96,65 +90,22 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
   float* const out_w = p.partials + size_t(cta) * WG_PARTIAL_FLOATS;
   float* const out_b = out_w + 65536;
   const RoleInfo R = role_info(role < 0 ? 0 : role, p.NH);
-  const bool fused = p.q.slots != nullptr;
   const uint32_t b_half_bytes = uint32_t(R.b_chunks) * WG_SUB * 128;
 
-  // ---- work list ----
-  // classic: tiles t = ridx + i*rcnt over the (at most two) segments.
-  // fused  : this consumer serves producers pr = ridx, ridx + rcnt, ... < NP; item i = (k, pr, g) with
-  //          k-major order (iteration k of every served producer, then k+1, ...), g = tile of the pair.
+  // work list: tiles t = ridx + i*rcnt over the (at most two) segments
   const long long total_tiles = p.seg_tiles[0] + p.seg_tiles[1];
-  const int n_mine = fused ? (p.q.NP > ridx ? (p.q.NP - ridx + rcnt - 1) / rcnt : 0) : 0;
-  const long long max_k = fused ? (p.num_iters + p.q.NP - 1) / p.q.NP : 0;
-  const long long n_items = role < 0 ? 0
-                            : (fused ? 2ll * n_mine * max_k
-                                     : ((total_tiles > ridx) ? (total_tiles - ridx + rcnt - 1) / rcnt : 0));
-  // queue of this role's streamed operand and which reader of it this role is
-  const int qi = (role == 9) ? 0 : (role == 7 ? 8 : (role == 8 ? 1 + (7 - 5) : 1 + (7 - (role + 1))));
-  const int reader = (role == 8) ? 1 : 0;
+  const long long n_items = role < 0 ? 0 : ((total_tiles > ridx) ? (total_tiles - ridx + rcnt - 1) / rcnt : 0);
 
   auto get_item = [&](long long i) -> WgItem {
     WgItem it;
-    it.wait_flag = nullptr;
-    it.done_flag = nullptr;
-    it.wait_val = it.done_val = 0;
-    long long t;   // global tile index (addresses the forward-saved arrays)
-    if (fused) {
-      const long long pair = i >> 1;
-      const int g = int(i & 1);
-      const long long kk = pair / n_mine;
-      const int pr = ridx + int(pair % n_mine) * rcnt;
-      const long long iter = pr + kk * p.q.NP;
-      it.valid = iter < p.num_iters;
-      t = iter * 2 + g;
-      const size_t qbase = (size_t(pr) * BWDW_QUEUES + qi) * 2;
-      const uint8_t* slot = p.q.slots + (qbase + g) * A_TILE_BYTES;
-      it.wait_flag = p.q.produced + qbase + g;
-      it.wait_val = uint32_t(kk + 1);
-      if (g == 1) {
-        it.done_flag = p.q.consumed + qbase + reader;
-        it.done_val = uint32_t(kk + 1);
-      }
-      const WgradSegment& sg = p.seg[0];
-      if (role == 9) {   // heads: A = h_7 (saved by the forward), B = dO (queue)
-        it.a_ptr = sg.h + (size_t(t) * NUM_TRUNK + 7) * A_TILE_BYTES;
-        it.b_ptr = slot;
-      } else {
-        it.a_ptr = slot;
-        it.b_ptr = (R.b_kind == 0) ? sg.h + (size_t(t) * NUM_TRUNK + R.b_layer) * A_TILE_BYTES
-                                   : sg.e + size_t(t) * E_TILE_BYTES;
-      }
-    } else {
-      t = ridx + i * rcnt;
-      it.valid = true;
-      const int seg = t < p.seg_tiles[0] ? 0 : 1;
-      const long long lt = seg ? t - p.seg_tiles[0] : t;
-      const WgradSegment& sg = p.seg[seg];
-      it.a_ptr = (R.a_kind == 0 ? sg.dz : sg.h) + (size_t(lt) * NUM_TRUNK + R.a_layer) * A_TILE_BYTES;
-      if (R.b_kind == 0) it.b_ptr = sg.h + (size_t(lt) * NUM_TRUNK + R.b_layer) * A_TILE_BYTES;
-      else if (R.b_kind == 1) it.b_ptr = sg.e + size_t(lt) * E_TILE_BYTES;
-      else it.b_ptr = sg.d_o + size_t(lt) * (2 * A_CHUNK_BYTES);
-    }
+    const long long t = ridx + i * rcnt;
+    const int seg = t < p.seg_tiles[0] ? 0 : 1;
+    const long long lt = seg ? t - p.seg_tiles[0] : t;
+    const WgradSegment& sg = p.seg[seg];
+    it.a_ptr = (R.a_kind == 0 ? sg.dz : sg.h) + (size_t(lt) * NUM_TRUNK + R.a_layer) * A_TILE_BYTES;
+    if (R.b_kind == 0) it.b_ptr = sg.h + (size_t(lt) * NUM_TRUNK + R.b_layer) * A_TILE_BYTES;
+    else if (R.b_kind == 1) it.b_ptr = sg.e + size_t(lt) * E_TILE_BYTES;
+    else it.b_ptr = sg.d_o + size_t(lt) * (2 * A_CHUNK_BYTES);
     return it;
   };
 
@@ -177,22 +128,10 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
     // ================================ loader ====================================
     // whole-warp control flow, one elected lane issues (see mlp_fwd.cu)
     uint32_t st = 0, phase = 0;
-    long long stall_cycles = 0, ring_cycles = 0;
-    const long long t_begin = clock64();
     for (long long i = 0; i < n_items; ++i) {
       const WgItem it = get_item(i);
-      if (!it.valid) continue;
-      if (it.wait_flag) {
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(it.wait_flag) < it.wait_val) {
-        }
-        stall_cycles += clock64() - t0;
-        fence_proxy_async_all();   // the producer's st.global data -> our bulk-copy (async proxy) reads
-      }
       for (int sub = 0; sub < 2; ++sub) {
-        const long long t1 = clock64();
         mbar_wait(smem_u32(&bars.empty[st]), phase ^ 1);
-        ring_cycles += clock64() - t1;
         if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&bars.full[st]), WG_HALF + b_half_bytes);
           const uint32_t dst = sbase + st * WG_STAGE_BYTES;
@@ -221,13 +160,6 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
         }
       }
     }
-    if (fused && p.q.stall && lane == 0) {
-      unsigned long long* s = p.q.stall + size_t(p.q.NP + cta) * 4;
-      s[0] = (unsigned long long)stall_cycles;     // waiting for producers
-      s[1] = (unsigned long long)ring_cycles;      // waiting for a free smem stage (MMA / bias warps behind)
-      s[2] = (unsigned long long)(clock64() - t_begin);
-      s[3] = (unsigned long long)role;
-    }
   } else if (warp == 5) {
     // ================================= MMA ======================================
     uint32_t st = 0, phase = 0;
@@ -238,14 +170,10 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
     constexpr uint64_t T_HI = make_sdesc_hi(512, LAYOUT_NONE) | (uint64_t(128 >> 4) << 16);
     bool first = true;
     for (long long i = 0; i < n_items; ++i) {
-      const WgItem it = get_item(i);
-      if (!it.valid) continue;
       for (int sub = 0; sub < 2; ++sub) {
         mbar_wait(smem_u32(&bars.full[st]), phase);
         tc_fence_after();
         if (elect_one()) {
-          // the stage has landed in shared memory: the queue slot may be rewritten by its producer
-          if (sub == 1 && it.done_flag) st_release_gpu(it.done_flag, it.done_val);
           const uint32_t a0 = sbase + st * WG_STAGE_BYTES;
           const uint64_t ad0 = (R.a_t ? T_HI : DESC_HI) | uint64_t((a0 >> 4) & 0x3FFF);
           const uint64_t bd0 = (R.b_t ? T_HI : DESC_HI) | uint64_t(((a0 + WG_HALF) >> 4) & 0x3FFF);
@@ -282,8 +210,6 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
     const uint32_t src_off = (R.bias_from_b ? WG_HALF : 0) + uint32_t(fp >> 5) * (WG_SUB * 128);
     const uint32_t unit = uint32_t(fp & 31) >> 2, wsel = uint32_t(fp & 3) * 4;
     for (long long i = 0; i < n_items; ++i) {
-      const WgItem it = get_item(i);
-      if (!it.valid) continue;
       any_mma = true;
       for (int sub = 0; sub < 2; ++sub) {
         mbar_wait(smem_u32(&bars.full[st]), phase);

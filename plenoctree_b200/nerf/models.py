@@ -10,7 +10,6 @@
 All arithmetic happens in the CUDA library behind the C ABI (include/plenoctree_b200.h); torch is
 used for device memory, streams and (in train.py) the NCCL all-reduce only.
 """
-import collections
 import math
 
 import numpy as np
@@ -20,8 +19,7 @@ from .. import _lib
 from .._lib import PREC_FP16, PREC_FP16X3, RenderConfig, check, lib, ptr, stream_ptr
 from ..layouts import K_of
 
-# nerf_sh/nerf/utils.py:53
-Rays = collections.namedtuple("Rays", ("origins", "directions", "viewdirs"))
+from .rays import Rays  # noqa: F401  (nerf_sh/nerf/utils.py:53)
 
 
 def _cuda_f32(t, name, shape_last=None):

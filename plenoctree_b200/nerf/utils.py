@@ -7,47 +7,7 @@
 """
 import numpy as np
 
-from .models import Rays  # noqa: F401
-
-
-def pose_spherical(theta, phi, radius):
-    """camera-to-world matrix looking at the origin (angles in degrees)."""
-    th, ph = np.deg2rad(theta), np.deg2rad(phi)
-    trans = np.eye(4, dtype=np.float64)
-    trans[2, 3] = radius
-    rot_phi = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1.0]])
-    rot_theta = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1.0]])
-    flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]])
-    return (flip @ rot_theta @ rot_phi @ trans).astype(np.float32)
-
-
-def generate_rays(w, h, focal, camtoworlds):
-    """per-pixel origins, un-normalised directions and unit viewdirs, each [n, h, w, 3]; pixel (x, y) on the
-    integer grid (no +0.5 centre shift, README.md:184)."""
-    x, y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing="xy")
-    cam = np.stack([(x - w * 0.5) / focal, -(y - h * 0.5) / focal, -np.ones_like(x)], axis=-1)
-    dirs = np.einsum("nij,hwj->nhwi", camtoworlds[:, :3, :3], cam).astype(np.float32)
-    origins = np.broadcast_to(camtoworlds[:, None, None, :3, 3], dirs.shape).astype(np.float32).copy()
-    viewdirs = dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)
-    return Rays(origins, dirs, viewdirs.astype(np.float32))
-
-
-def random_rays_np(n, seed, w=800, h=800, camera_angle_x=0.6911112070083618, radius=4.0, n_poses=100):
-    """Synthetic benchmark rays: n_poses random spherical poses (theta ~ U(-180,180),
-    phi ~ U(-90,0)), each ray = one uniformly random pixel of one random pose; targets ~ U[0,1).
-    Returns origins, directions, viewdirs, pixels as float32 [n,3] arrays."""
-    rs = np.random.RandomState(seed)
-    focal = 0.5 * w / np.tan(0.5 * camera_angle_x)
-    poses = np.stack([pose_spherical(rs.uniform(-180, 180), rs.uniform(-90, 0), radius) for _ in range(n_poses)])
-    pi = rs.randint(0, n_poses, size=n)
-    x = rs.randint(0, w, size=n).astype(np.float32)
-    y = rs.randint(0, h, size=n).astype(np.float32)
-    cam = np.stack([(x - w * 0.5) / focal, -(y - h * 0.5) / focal, -np.ones_like(x)], axis=-1).astype(np.float32)
-    d = np.einsum("nij,nj->ni", poses[pi, :3, :3], cam).astype(np.float32)
-    o = poses[pi, :3, 3].astype(np.float32)
-    v = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
-    px = rs.uniform(0, 1, size=(n, 3)).astype(np.float32)
-    return o, d, v, px
+from .rays import Rays, generate_rays, pose_spherical, random_rays_np  # noqa: F401  (numpy only)
 
 
 def render_image(model, rays, normalize_disp=False, chunk=8192, precision=None):
