@@ -9,6 +9,14 @@
 // swizzled tile-image format as the forward activations; mlp_wgrad contracts them over samples.
 // No gradient w.r.t. the inputs is needed (layer 0 and the skip slice of layer 5 stop here).
 //
+// Warp roles (576 threads): warps 0-3 / 4-7 = epilogue groups of tile X / Y (TMEM lane i <-> sample row i),
+// warp 8 = weight producer, warp 9 = MMA issuer (peer CTA: relay), warps 10-13 / 14-17 = copy-out warps of tile
+// X / Y.  The finished dZ_l (dO) tile must leave the SM: 64 KB per tile and GEMM against ~25-30 B/clk of SM store
+// bandwidth (scripts/overlap_probe.cu) is longer than the GEMM itself, and a warp that issues st.global into a
+// full store queue stalls — so the epilogue warps never store.  They hand the tile to the MMA warp AND to their
+// copy warps; those pull it into registers half a tile at a time (the shared-memory tile is free again ~2.6 k
+// cycles after the hand-over, well before the next epilogue needs it) and let the stores drain from registers.
+//
 // PAIR (default): two CTAs of a cluster share one tcgen05.mma.cta_group::2 stream over four tiles
 // (512 samples per iteration), each CTA holding half of every transposed-weight slot — same protocol
 // as mlp_fwd.cu (leader issues, peer relays landed half-slots, commits multicast to both CTAs).
@@ -21,7 +29,8 @@ namespace pob {
 
 namespace {
 
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 576;
+constexpr int BWD_COPY_WARP0 = 10;     // first copy-out warp
 constexpr int BWD_PRODUCER_WARP = 8;
 constexpr int BWD_MMA_WARP = 9;
 constexpr int BWD_WSLOTS = 6;            // 16 KB slots (single CTA) or twice as many 8 KB half-slots (pair)
@@ -38,6 +47,8 @@ struct BwdBarriers {
   uint64_t pfull[BWD_MAX_RING];
   uint64_t a_ready[2];
   uint64_t d_ready[2];
+  uint64_t c_ready[2];   // epilogue group -> copy warps: tile written (4 arrivals)
+  uint64_t c_free[2][2]; // copy warps -> epilogue group: first / second half of the tile pulled into registers
 };
 
 __device__ __forceinline__ void bwd_stamp(unsigned long long* tr, int role, uint32_t& n) {
@@ -74,6 +85,9 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
     for (int g = 0; g < 2; ++g) {
       mbar_init(smem_u32(&bars.a_ready[g]), PAIR ? 8 : 4);
       mbar_init(smem_u32(&bars.d_ready[g]), 1);
+      mbar_init(smem_u32(&bars.c_ready[g]), 4);
+      mbar_init(smem_u32(&bars.c_free[g][0]), 4);
+      mbar_init(smem_u32(&bars.c_free[g][1]), 4);
     }
     fence_mbar_init();
   }
@@ -174,29 +188,79 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
         }
       }
     }
+  } else if (warp >= BWD_COPY_WARP0) {
+    // ================================ copy-out warps ====================================
+    // warp q of tile g copies a quarter of each HALF of every finished tile image (linear: 512 contiguous bytes
+    // per warp instruction) through 64 registers: the first half of the image — which the next epilogue rewrites
+    // first — is released as soon as it has been read, the second half once the first half's stores are queued.
+    const int g = (warp - BWD_COPY_WARP0) >> 2, q = (warp - BWD_COPY_WARP0) & 3;
+    const uint8_t* const a_tile = smem + (g ? SB_A1 : SB_A0);
+    uint32_t cphase = 0;
+    for (long long it = unit; it < num_iters; it += nunits) {
+      const long long tile_idx = it * TILES_PER_ITER + (PAIR ? int(rank) * 2 : 0) + g;
+      for (int k = 0; k <= NUM_TRUNK; ++k) {          // dO, dZ_7 .. dZ_0
+        const uint32_t half = (k == 0 ? uint32_t(do_chunks) * A_CHUNK_BYTES : uint32_t(A_TILE_BYTES)) / 2;   // 8, 16 or 32 KB
+        const uint32_t share = half / 4;                                                                     // 2, 4 or 8 KB
+        uint8_t* const dst = (k == 0 ? p.save_do + size_t(tile_idx) * (2 * A_CHUNK_BYTES)
+                                     : p.save_dz + (size_t(tile_idx) * NUM_TRUNK + (NUM_TRUNK - k)) * A_TILE_BYTES) +
+                             q * share + lane * 16;
+        const uint8_t* const src = a_tile + q * share + lane * 16;
+        mbar_wait(smem_u32(&bars.c_ready[g]), cphase);
+        cphase ^= 1;
+        uint4 r[16];
+        const int nu = int(share / 512);               // 512-byte rows per batch: 4, 8 or 16
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nu) r[i] = *reinterpret_cast<const uint4*>(src + b * half + i * 512);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars.c_free[g][b]));
+          if (!(p.debug_flags & 1)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nu) *reinterpret_cast<uint4*>(dst + b * half + i * 512) = r[i];
+          }
+        }
+      }
+    }
   } else {
+    // ================================ epilogue warps ====================================
     const int g = warp >> 2;
     uint32_t tn = 0;
     unsigned long long* const tre = (warp == 0 && lane == 0) ? p.trace : nullptr;
     const int row = int((warp & 3) * 32 + lane);
     uint8_t* const a_tile = smem + (g ? SB_A1 : SB_A0);
     const uint32_t d_tmem = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(g) * 256u;
-    uint32_t dphase = 0;
+    uint32_t dphase = 0, fphase = 0;
+    bool first_tile = true;
     const uint32_t a_ready_addr = (PAIR && rank != 0) ? mapa_cluster(smem_u32(&bars.a_ready[g]), 0)
                                                       : smem_u32(&bars.a_ready[g]);
-    auto signal_a_ready = [&]() {
+    // hand the finished tile to the MMA warp (unless it is dZ_0: no GEMM follows) and to the copy warps
+    auto hand_over = [&](bool to_mma) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster_any(a_ready_addr, rank != 0);
-        else mbar_arrive(a_ready_addr);
+        if (to_mma) {
+          if (PAIR) mbar_arrive_cluster_any(a_ready_addr, rank != 0);
+          else mbar_arrive(a_ready_addr);
+        }
+        mbar_arrive(smem_u32(&bars.c_ready[g]));
+      }
+    };
+    // before the first write into a half of a_tile: the copy warps have pulled that half of the previous tile
+    // into registers (the parity flips after the second half)
+    auto wait_half_free = [&](int h) {
+      if (!first_tile) mbar_wait(smem_u32(&bars.c_free[g][h]), fphase);
+      if (h == 1) {
+        if (!first_tile) fphase ^= 1;
+        first_tile = false;
       }
     };
 
-    // Global loads of an iteration (per-sample gradient, view direction, ReLU masks) are issued one step AHEAD of
-    // their use: a load issued behind this warp's 64 KB tile copy-outs waits in the same LSU queue until those
-    // stores have drained (thousands of cycles), which used to stall every epilogue at its first mask bit.
+    // Global loads of an iteration (per-sample gradient, view direction, ReLU masks) are issued one step ahead
+    // of their use.
     auto sample_of = [&](long long it_) { return (it_ * TILES_PER_ITER + (PAIR ? int(rank) * 2 : 0) + g) * TILE_M + row; };
     auto mask_ptr = [&](int l, long long s_) { return reinterpret_cast<const uint4*>(p.mask + (size_t(l) * mrows + s_) * 8); };
     float4 gq_n = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -228,9 +292,8 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
         basis[0] = 1.f;
         if (s < p.M && p.sh_deg >= 0) sh_basis(p.sh_deg, vd_n[0], vd_n[1], vd_n[2], basis);
         const float gc[3] = {gq.x, gq.y, gq.z};
-        uint8_t* const do_glob = p.save_do + size_t(tile_idx) * (2 * A_CHUNK_BYTES);
-        // every warp of the group must be done copying the previous iteration's dZ_0 image out of a_tile
-        named_bar_sync(1 + g, 128);
+        wait_half_free(0);
+        wait_half_free(1);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {            // 16-byte units of 8 columns, up to 128 columns
           if (u * 8 < do_chunks * 64) {
@@ -256,16 +319,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
             *reinterpret_cast<uint4*>(a_tile + off) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        signal_a_ready();
-        // dO tile -> global (after the hand-over, overlapping the heads dgrad GEMM)
-        named_bar_sync(1 + g, 128);
-        {
-          const int t = int(threadIdx.x & 127);
-          const uint4* src = reinterpret_cast<const uint4*>(a_tile) + t;
-          uint4* dst = reinterpret_cast<uint4*>(do_glob) + t;
-          for (int i = 0; i < do_chunks * (A_CHUNK_BYTES / 16 / 128); ++i) dst[i * 128] = src[i * 128];
-        }
-        named_bar_sync(1 + g, 128);   // every thread of the group is done reading a_tile
+        hand_over(true);
       }
       // ---- dZ_7 .. dZ_0 ----
       for (int l = NUM_TRUNK - 1; l >= 0; --l) {
@@ -276,52 +330,46 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
         tc_fence_after();
         bwd_stamp(tre, 1, tn);                          // d_ready observed
         if (p.debug_flags & 2) {
-        } else if (l > 0) {   // next layer's mask: issued before this layer's copy-out stores are queued
+        } else if (l > 0) {
           mn0 = __ldg(mask_ptr(l - 1, s));
           mn1 = __ldg(mask_ptr(l - 1, s) + 1);
         } else if (it + nunits < num_iters) {
           prefetch_iter(it + nunits);
         }
-        uint8_t* const dz_glob = p.save_dz + (size_t(tile_idx) * NUM_TRUNK + l) * A_TILE_BYTES;
-        uint32_t va[32], vb[32];
-        tmem_ld32(d_tmem, va);
+        // the previous tile is dO for l = 7: its (smaller) image lies entirely inside this tile's first half
+        wait_half_free(0);
+        if (l == NUM_TRUNK - 1) wait_half_free(1);
+        uint32_t va[16], vb[16];
+        tmem_ld16(d_tmem, va);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t(&v)[32] = (c & 1) ? vb : va;
+        for (int c = 0; c < 16; ++c) {                  // 16 accumulator columns at a time
+          uint32_t(&v)[16] = (c & 1) ? vb : va;
+          if (c == 8 && l != NUM_TRUNK - 1) wait_half_free(1);   // columns 128.. live in the second half of the image
           tmem_ld_wait();
-          if (c + 1 < 8) tmem_ld32(d_tmem + (c + 1) * 32, (c & 1) ? va : vb);   // prefetch next chunk
-          const uint32_t m = mw[c];
+          if (c + 1 < 16) tmem_ld16(d_tmem + (c + 1) * 16, (c & 1) ? va : vb);   // prefetch next chunk
+          const uint32_t m = mw[c >> 1];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int e0 = 8 * u + 2 * i, k = 4 * u + i;
-              const float f0 = (m & (0x00008000u >> k)) ? __uint_as_float(v[e0]) : 0.f;
-              const float f1 = (m & (0x80000000u >> k)) ? __uint_as_float(v[e0 + 1]) : 0.f;
-              w[i] = pack_f16x2(f0, f1);
+              // word k of the 32-column group: flags at bits 15-k / 31-k -> shifted to the byte sign bits 15 / 31,
+              // replicated over the two halves by PRMT, ANDed onto the packed fp16 pair
+              const int k = (c & 1) * 8 + 4 * u + i;
+              uint32_t keep;   // bytes 0,1 <- sign of byte 1, bytes 2,3 <- sign of byte 3 (prmt sign-replicate mode)
+              asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(keep) : "r"(m << k));
+              w[i] = pack_f16x2(__uint_as_float(v[8 * u + 2 * i]), __uint_as_float(v[8 * u + 2 * i + 1])) & keep;
             }
-            const uint32_t unit_ = uint32_t((c & 1) * 4 + u);
-            const uint32_t off = uint32_t(c >> 1) * A_CHUNK_BYTES + uint32_t(row) * 128u +
+            const uint32_t unit_ = uint32_t((c & 3) * 2 + u);
+            const uint32_t off = uint32_t(c >> 2) * A_CHUNK_BYTES + uint32_t(row) * 128u +
                                  ((unit_ ^ uint32_t(row & 7)) << 4);
             *reinterpret_cast<uint4*>(a_tile + off) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
         bwd_stamp(tre, 1, tn);                          // accumulator drained, dZ tile written
-        if (l > 0) signal_a_ready();
-        else fence_proxy_async_smem();
+        hand_over(l > 0);
         bwd_stamp(tre, 1, tn);                          // handed over
-        // dZ_l tile -> global after the hand-over: the copy overlaps the next GEMM (see mlp_fwd.cu)
-        named_bar_sync(1 + g, 128);
-        if (!(p.debug_flags & 1)) {
-          const int t = int(threadIdx.x & 127);
-          const uint4* src = reinterpret_cast<const uint4*>(a_tile) + t;
-          uint4* dst = reinterpret_cast<uint4*>(dz_glob) + t;
-#pragma unroll 8
-          for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) dst[i * 128] = src[i * 128];
-        }
-        named_bar_sync(1 + g, 128);   // the next epilogue may overwrite a_tile
-        bwd_stamp(tre, 1, tn);                          // tile copied out
+        bwd_stamp(tre, 1, tn);
       }
     }
   }

@@ -29,7 +29,7 @@ t0 = t[t > 0].min()
 mma = t[0][t[0] > 0] - t0
 e = t[1][t[1] > 0] - t0
 mm = mma[: (len(mma) // 2) * 2].reshape(-1, 2)     # per GEMM: [operand X observed, all issued]
-ee = e[: (len(e) // 4) * 4].reshape(-1, 4)         # per dZ layer: [d_ready, drained, handed over, copied out]
+ee = e[: (len(e) // 4) * 4].reshape(-1, 4)         # per dZ layer: [d_ready, drained, handed over, (unused)]
 n = min(len(ee), 24)
 epi = (ee[:n, 1] - ee[:n, 0]); sig = (ee[:n, 2] - ee[:n, 1]); cp = (ee[:n, 3] - ee[:n, 2])
 ph = (mm[:, 1] - mm[:, 0])
