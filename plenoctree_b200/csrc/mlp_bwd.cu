@@ -44,7 +44,6 @@ constexpr uint32_t SB_TOTAL = SB_W + BWD_WSLOTS * WSLOT_BYTES;  // 128K + 96K = 
 struct BwdBarriers {
   uint64_t full[BWD_MAX_RING];
   uint64_t empty[BWD_MAX_RING];
-  uint64_t pfull[BWD_MAX_RING];
   uint64_t a_ready[2];
   uint64_t d_ready[2];
   uint64_t c_ready[2];   // epilogue group -> copy warps: tile written (4 arrivals)
@@ -78,9 +77,9 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) {
-      mbar_init(smem_u32(&bars.full[i]), 1);
+      // pair mode, leader: a slot is full when its own half has landed AND the peer has reported its half
+      mbar_init(smem_u32(&bars.full[i]), (PAIR && rank == 0) ? 2 : 1);
       mbar_init(smem_u32(&bars.empty[i]), 1);
-      mbar_init(smem_u32(&bars.pfull[i]), 1);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(smem_u32(&bars.a_ready[g]), PAIR ? 8 : 4);
@@ -126,7 +125,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
   } else if (warp == BWD_MMA_WARP) {
     uint32_t slot = 0, phase = 0, aphase = 0;
     if (PAIR && rank != 0) {
-      const uint32_t pfull0 = mapa_cluster(smem_u32(&bars.pfull[0]), 0);
+      const uint32_t pfull0 = mapa_cluster(smem_u32(&bars.full[0]), 0);
       const int nslots = hs + 7 * 8;
       for (long long it = unit; it < num_iters; it += nunits) {
         for (int j = 0; j < nslots; ++j) {
@@ -140,6 +139,11 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
         }
       }
     } else {
+      // Tile X and tile Y take turns on the tensor core, one whole GEMM at a time: while Y's MMAs run, X's
+      // epilogue drains X's accumulator and writes X's next operand tile, and vice versa, so the tensor pipe
+      // does not idle through the epilogues (lock-step tiles: MMA 4.4 k + epilogue 1.8 k cycles per GEMM pair).
+      // Every weight slot is streamed once and read twice, by X and — one GEMM (ns slots) later — by Y; the
+      // ring (12 half-slots in pair mode) holds the GEMM's 8 slots plus 4 of prefetch.
       const uint32_t idesc = make_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, WIDTH);
       constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
       constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
@@ -148,39 +152,50 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
       for (long long it = unit; it < num_iters; it += nunits) {
         for (int grp = 0; grp < 8; ++grp) {      // heads, then Dense_7 .. Dense_1
           const int ns = (grp == 0) ? hs : 8;
-          for (int j = 0; j < ns; ++j) {
-            const uint32_t a_off = uint32_t(j >> 1) * A_CHUNK_BYTES + uint32_t(j & 1) * 64u;
-            mbar_wait(smem_u32(&bars.full[slot]), phase);
-            if (PAIR) mbar_wait(smem_u32(&bars.pfull[slot]), phase);
-            const uint64_t bd0 = W_HI | uint64_t(((sbase + SB_W + slot * RSLOT_BYTES) >> 4) & 0x3FFF);
+          // slots per turn: the whole GEMM when the ring can hold it (pair mode: 12 half-slots), else 2
+          constexpr int TURN = PAIR ? 8 : 2;
+          for (int j0 = 0; j0 < ns; j0 += TURN) {
+            const int j1 = j0 + TURN < ns ? j0 + TURN : ns;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              if (j == 0) {
+              uint32_t rs = slot, rph = phase;   // ring position of the turn's first slot
+              if (j0 == 0) {
                 wait_bar(&bars.a_ready[g], aphase);
-                if (g == 0) bwd_stamp(trm, 0, tn);      // tile X's operand observed
+                if (g == 0) bwd_stamp(trm, 0, tn);        // tile X's operand observed
               }
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t a_base = sbase + (g ? SB_A1 : SB_A0) + a_off;
-                const uint64_t ad0 = A_HI | uint64_t((a_base >> 4) & 0x3FFF);
-                const uint32_t d = tmem + uint32_t(g) * 256u;
-                if (PAIR) {
-                  umma_f16_pair(d, ad0, bd0, idesc, j != 0);
-                  umma_f16_pair(d, ad0 + 2, bd0 + 2, idesc, 1u);
-                  if (j == ns - 1) umma_commit_pair(smem_u32(&bars.d_ready[g]), 0x3);
-                  if (g == 1) umma_commit_pair(smem_u32(&bars.empty[slot]), 0x3);
-                } else {
-                  umma_f16(d, ad0, bd0, idesc, j != 0);
-                  umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
-                  if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
-                  if (g == 1) umma_commit(smem_u32(&bars.empty[slot]));
+              for (int j = j0; j < j1; ++j) {
+                const uint32_t a_off = uint32_t(j >> 1) * A_CHUNK_BYTES + uint32_t(j & 1) * 64u;
+                if (g == 0) {                    // the slot lands once; Y finds it in place
+                  mbar_wait(smem_u32(&bars.full[rs]), rph);
+                }
+                const uint64_t bd0 = W_HI | uint64_t(((sbase + SB_W + rs * RSLOT_BYTES) >> 4) & 0x3FFF);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t a_base = sbase + (g ? SB_A1 : SB_A0) + a_off;
+                  const uint64_t ad0 = A_HI | uint64_t((a_base >> 4) & 0x3FFF);
+                  const uint32_t d = tmem + uint32_t(g) * 256u;
+                  if (PAIR) {
+                    umma_f16_pair(d, ad0, bd0, idesc, j != 0);
+                    umma_f16_pair(d, ad0 + 2, bd0 + 2, idesc, 1u);
+                    if (j == ns - 1) umma_commit_pair(smem_u32(&bars.d_ready[g]), 0x3);
+                    if (g == 1) umma_commit_pair(smem_u32(&bars.empty[rs]), 0x3);
+                  } else {
+                    umma_f16(d, ad0, bd0, idesc, j != 0);
+                    umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+                    if (j == ns - 1) umma_commit(smem_u32(&bars.d_ready[g]));
+                    if (g == 1) umma_commit(smem_u32(&bars.empty[rs]));
+                  }
+                }
+                __syncwarp();
+                if (++rs == RING) {
+                  rs = 0;
+                  rph ^= 1;
                 }
               }
-              __syncwarp();
-            }
-            if (++slot == RING) {
-              slot = 0;
-              phase ^= 1;
+              if (g == 1) {
+                slot = rs;
+                phase = rph;
+              }
             }
           }
           aphase ^= 1;

@@ -56,7 +56,6 @@ constexpr int MAX_RING = 8;   // pair mode: eight 8 KB half-slots in the same 64
 struct Barriers {
   uint64_t full[MAX_RING];
   uint64_t empty[MAX_RING];
-  uint64_t pfull[MAX_RING];   // pair mode, leader only: the peer's half of the slot has landed
   uint64_t a_ready[2];
   uint64_t d_ready[2];
 };
@@ -166,6 +165,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
   constexpr bool PRECISE = (NSPLIT == 3);
   __shared__ __align__(8) Barriers bars;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) uint4 slot_tab[FWD_TRUNK_SLOTS + FWD_HEAD_SLOTS + 1];   // MMA issue table (see the MMA warp)
 
   constexpr int NTILES = (NSPLIT == 1) ? 2 : 1;                       // tiles per CTA and iteration
   constexpr int TILES_PER_ITER = PAIR ? 4 : NTILES;                   // tiles per scheduling unit (CTA or pair)
@@ -181,9 +181,9 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) {
-      mbar_init(smem_u32(&bars.full[i]), 1);
+      // pair mode, leader: a slot is full when its own half has landed AND the peer has reported its half
+      mbar_init(smem_u32(&bars.full[i]), (PAIR && rank == 0) ? 2 : 1);
       mbar_init(smem_u32(&bars.empty[i]), 1);
-      mbar_init(smem_u32(&bars.pfull[i]), 1);
     }
     for (int g = 0; g < 2; ++g) {
       // one arrival per epilogue warp that writes the operand tile(s) the MMA reads: 4 (own tile), 8 in the
@@ -250,7 +250,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
     uint32_t slot = 0, phase = 0, aphase = 0, tn = 0;
     if (PAIR && rank != 0) {
       // peer CTA: no MMAs to issue; relay every landed half-slot to the leader's pfull barrier
-      const uint32_t pfull0 = mapa_cluster(smem_u32(&bars.pfull[0]), 0);
+      const uint32_t pfull0 = mapa_cluster(smem_u32(&bars.full[0]), 0);
       for (long long it = unit; it < num_iters; it += nunits) {
         for (int l = 0; l <= NUM_TRUNK; ++l) {
           const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
@@ -271,6 +271,90 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
     constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
     constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
     const uint32_t w_base = sbase + SM_W;
+    if (NSPLIT == 1) {
+      // Tiles X and Y take turns of TURN weight slots on the tensor core: X's layer ends one turn before Y's,
+      // so X's epilogue (accumulator drain, next operand tile) runs under Y's last turn and Y's under the first
+      // turn of X's next layer — the tensor pipe no longer idles through every epilogue (lock-step tiles: 4.4 k
+      // cycles of MMAs + 1.3 k of epilogue per layer).  Every weight slot is still streamed once: it stays in
+      // the ring from X's use to Y's, TURN slots later (pair mode: 5 of the 8 half-slots live, 3 of prefetch).
+      // The issue loop must average < 256 cycles per (tile, slot) = two MMAs, so everything that depends on the
+      // layer structure (which tile image feeds K-slot j, bias slots, layer ends) is tabulated once per CTA.
+      constexpr int TURN = PAIR ? 5 : 2;
+      for (int n = int(lane); n < FWD_TRUNK_SLOTS + FWD_HEAD_SLOTS; n += 32) {
+        int l = 0, j = n;
+        while (l < NUM_TRUNK && j >= fwd_slots_of_layer(l)) j -= fwd_slots_of_layer(l++);
+        const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
+        // A operand of K-slot j: the previous layer's activations, or the posenc tile for layer 0, the skip slots
+        // of layer 5, and the bias slot (j == 8) of every other layer, which only multiplies the k16 group
+        // [48,64) of the posenc tile (column 63 = 1) with its row k = 31.
+        const bool bias_slot = (l == NUM_TRUNK || fwd_has_bias_slot(l)) && j == 8;
+        const bool from_e = (l == 0) || j >= 8;
+        const int kk = bias_slot ? 1 : ((l == SKIP_LAYER && j >= 8) ? j - 8 : j);
+        const uint32_t a_off = uint32_t(kk >> 1) * A_CHUNK_BYTES + uint32_t(kk & 1) * 64u;
+        uint4 e;
+        e.x = ((sbase + (from_e ? SM_E0 : SM_A0) + a_off) >> 4) & 0x3FFF;
+        e.y = ((sbase + (from_e ? SM_E1 : SM_A1) + a_off) >> 4) & 0x3FFF;
+        e.z = (bias_slot ? 1u : 0u) | (j != 0 ? 2u : 0u) | (j == ns - 1 ? 4u : 0u) | (l == NUM_TRUNK ? 8u : 0u);
+        e.w = 0;
+        slot_tab[n] = e;
+      }
+      __syncwarp();
+      const uint32_t w_enc0 = (w_base >> 4) & 0x3FFF;
+      for (long long it = unit; it < num_iters; it += nunits) {
+        int n0 = 0;                               // table index of the layer's first slot
+        for (int l = 0; l <= NUM_TRUNK; ++l) {
+          const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
+          for (int j0 = 0; j0 < ns; j0 += TURN) {
+            const int j1 = j0 + TURN < ns ? j0 + TURN : ns;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t rs = slot, rph = phase;   // ring position of the turn's first slot
+              if (j0 == 0) {
+                wait_bar(&bars.a_ready[g], aphase);   // tile g's operand tile written, D drained (both CTAs)
+                if (g == 0) trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);
+              }
+              uint4 e = slot_tab[n0 + j0];
+              for (int j = j0; j < j1; ++j) {
+                const uint4 en = slot_tab[n0 + j + 1];   // (one spare entry behind the table)
+                if (g == 0) mbar_wait(smem_u32(&bars.full[rs]), rph);   // the slot lands once; Y finds it in place
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t ah0 = A_HI | uint64_t(g ? e.y : e.x);
+                  const uint64_t bh0 = W_HI | uint64_t(w_enc0 + rs * (RSLOT_BYTES >> 4));
+                  const uint32_t d = tmem + uint32_t(g) * 256u;
+                  const uint32_t idesc = (e.z & 8u) ? idesc_h : idesc_t;
+                  if (PAIR) {
+                    // M = 256: rows 0-127 = this CTA's tile g, rows 128-255 = the peer's tile g (same offsets)
+                    if (!(e.z & 1u)) umma_f16_pair(d, ah0, bh0, idesc, e.z & 2u);
+                    umma_f16_pair(d, ah0 + 2, bh0 + 2, idesc, 1u);
+                    if (e.z & 4u) umma_commit_pair(smem_u32(&bars.d_ready[g]), 0x3);
+                    if (g == 1) umma_commit_pair(smem_u32(&bars.empty[rs]), 0x3);
+                  } else {
+                    if (!(e.z & 1u)) umma_f16(d, ah0, bh0, idesc, e.z & 2u);
+                    umma_f16(d, ah0 + 2, bh0 + 2, idesc, 1u);      // k16 step 1: +32 bytes = +2 encoded
+                    if (e.z & 4u) umma_commit(smem_u32(&bars.d_ready[g]));
+                    if (g == 1) umma_commit(smem_u32(&bars.empty[rs]));
+                  }
+                }
+                __syncwarp();
+                e = en;
+                if (++rs == RING) {
+                  rs = 0;
+                  rph ^= 1;
+                }
+              }
+              if (g == 1) {
+                slot = rs;
+                phase = rph;
+              }
+            }
+          }
+          n0 += ns;
+          aphase ^= 1;
+          trace_stamp(lane == 0 ? p.trace : nullptr, 0, tn);       // all MMAs of the layer issued
+        }
+      }
+    } else
     for (long long it = unit; it < num_iters; it += nunits) {
       for (int l = 0; l <= NUM_TRUNK; ++l) {
         const int ns = (l == NUM_TRUNK) ? FWD_HEAD_SLOTS : fwd_slots_of_layer(l);
@@ -286,7 +370,6 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
           const uint32_t s_hi = slot;
           const uint32_t s_lo = slot + 1;  // x3 only; ring depth is even: hi/lo never straddle the wrap
           mbar_wait(smem_u32(&bars.full[s_hi]), phase);
-          if (PAIR) mbar_wait(smem_u32(&bars.pfull[s_hi]), phase);   // the peer's half of the slot
           if (NSPLIT == 3) mbar_wait(smem_u32(&bars.full[s_lo]), phase);
           const uint64_t bh0 = W_HI | uint64_t(((w_base + s_hi * RSLOT_BYTES) >> 4) & 0x3FFF);
           const uint64_t bl0 = W_HI | uint64_t(((w_base + s_lo * RSLOT_BYTES) >> 4) & 0x3FFF);
@@ -444,7 +527,8 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
           // stage of the training forward: it has the whole MMA phase to drain.  Measured alternatives
           // (scripts/overlap_probe.cu, profiles/r2_overlap_probe.json): stores issued from inside the epilogue stall
           // it, because a backed-up st.global queue blocks the warp's later st.shared / fences; a TMA bulk store of the
-          // tile collides with the weight-slot TMA loads (258 vs 170 cycles per MMA).
+          // verbatim tile image (no LSU time at all) collides with the weight-slot TMA loads and with the MMA operand
+          // reads: 73.5 k vs 63.1 k cycles per iteration (tried in round 2, removed).
           // debug flag 16 (timing experiment): every h store lands in one 64 KB scratch tile per CTA (L2, not HBM)
           uint8_t* const h_glob = p.save_h + ((p.debug_flags & 16) ? size_t(blockIdx.x)
                                                                    : (size_t(tile_idx) * NUM_TRUNK + l)) * A_TILE_BYTES;

@@ -24,6 +24,7 @@ struct Args {
   int n_mma;               // MMAs to issue (in batches of 32 with a commit + wait each)
   int store_mode;
   int with_weights;        // stream one 16 KB (8 KB in pair mode) slot per 4 MMAs
+  int n_cols;              // MMA N (256 or 128)
   unsigned long long* res; // [cta][4]: mma cycles, stored bytes, store cycles
 };
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ void body(const Args& a, uint8_t* smem) {
     }
   } else if (warp == 9) {     // MMA issuer
     if (!PAIR || rank == 0) {
-      const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, 256);
+      const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, a.n_cols);
       constexpr uint64_t A_HI = make_sdesc_hi(1024, LAYOUT_SW128) | (uint64_t(1) << 16);
       constexpr uint64_t W_HI = make_sdesc_hi(512, LAYOUT_SW64) | (uint64_t(1) << 16);
       uint32_t slot = 0, phase = 0, dphase = 0;
@@ -184,7 +185,9 @@ int main() {
       for (int l2 = 0; l2 < 2; ++l2)
         for (int mode = 0; mode < 6; ++mode) {
           if (mode == 0 && l2) continue;
+          if (getenv("PROBE_QUICK") && !(mode == 0 && weights == 0)) continue;
           a.n_mma = 16384;
+          a.n_cols = 256;
           a.store_mode = mode;
           a.with_weights = weights;
           a.wrap = l2 ? 131072 : stride;   // L2-resident destination vs streaming to HBM
@@ -205,5 +208,17 @@ int main() {
                  pair, weights, l2 ? "L2" : "HBM", names[mode], mc / nm / a.n_mma, sc > 0 ? sb / sc * 1.0 : 0.0);
           fflush(stdout);
         }
+  for (int pair = 0; pair < 2; ++pair) {
+    a.n_mma = 16384; a.n_cols = 128; a.store_mode = 0; a.with_weights = 0; a.wrap = stride;
+    CK(cudaMemset(a.res, 0, sizeof(unsigned long long) * 4 * sms));
+    for (int rep = 0; rep < 2; ++rep) {
+      if (pair) probe_pair<<<sms, 320, P_TOTAL>>>(a); else probe_single<<<sms, 320, P_TOTAL>>>(a);
+      CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(h, a.res, sizeof(unsigned long long) * 4 * sms, cudaMemcpyDeviceToHost));
+    double mc = 0; int nm = 0;
+    for (int i = 0; i < sms; ++i) if (h[i * 4]) { mc += double(h[i * 4]); ++nm; }
+    printf("{\"pair\": %d, \"mma_n\": 128, \"cycles_per_mma\": %.1f}\n", pair, mc / nm / a.n_mma);
+  }
   return 0;
 }
