@@ -16,9 +16,11 @@ sparsity points per step (the reference draws those per device, nerf_sh/train.py
 `value`  : rays/s with the step's rays already resident in HBM (CUDA events, max over ranks).
 `e2e`    : rays/s through the host-facing API with the rays/pixels of every step copied from pinned host
            memory and the step's loss statistics read back to the host inside the timed region.
-`roofline`: dominant kernel class, algorithmic GEMM FLOPs (1,007,104 fwd / 942,592 dgrad /
-           1,007,104 wgrad FLOP per MLP-sample, SH16) / CUDA-event kernel time, vs the measured
-           sustained bf16 tensor peak in MEASURED_PEAKS.json.
+`roofline`: dominant kernel class (and, under `kernels`, all three), algorithmic GEMM FLOPs (SURVEY.md §8d:
+           1,007,104 fwd / 942,592 dgrad / 1,007,104 wgrad FLOP per MLP-sample, SH16) / CUDA-event kernel time,
+           vs the measured sustained bf16 tensor peak in MEASURED_PEAKS.json; `step_frac` = the whole step.
+`strong`, `tt_sh25`, `c4_extraction`, `c5_octree_opt`: the other BASELINE configurations, timed after the main
+           region on the same ranks (bench_extras.py); skipped with --no-extras.
 """
 import argparse
 import ctypes
@@ -193,6 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / SH25 / extraction / octree extras")
     ap.add_argument("--workload", default="blender", choices=["blender", "tt"],
                     help="blender = BASELINE configs[1] (SH16, near/far 2/6; the default and the quoted metric); "
                          "tt = configs[2] (SH25, near/far 0/4, sparsity radius 5 / length 0.2)")
@@ -207,7 +210,7 @@ def main():
     from plenoctree_b200 import _lib
     from plenoctree_b200.nerf import train as T
     from plenoctree_b200.nerf.models import NerfModel, Rays
-    from plenoctree_b200.nerf.utils import random_rays_np
+    from plenoctree_b200.nerf.rays import random_rays_np
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -339,13 +342,35 @@ def main():
     dom = max(alg, key=lambda k: per_step_ms[k])
     peaks = measured_peaks()
     achieved = alg[dom] / (per_step_ms[dom] * 1e-3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel class, per step, from the committed
-    # `ncu --set full` capture (profiles/r1_dram_traffic.json; scaled there to the 4096-ray step)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+    # dram__bytes_read.sum + dram__bytes_write.sum per kernel class and step, from the committed `ncu --set full`
+    # capture of this round (profiles/r2_dram_traffic.json; scaled there to the 4096-ray step)
+    traffic_all = {}
+    for name in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            traffic_all = json.load(open(tpath))
+            break
+    traffic = traffic_all.get(dom)
+    kernels = {k: {"ms_per_step": per_step_ms[k], "algorithmic_flops_per_step": alg[k],
+                   "achieved": alg[k] / (per_step_ms[k] * 1e-3) / 1e12,
+                   "frac": alg[k] / (per_step_ms[k] * 1e-3) / 1e12 / peaks["tflops"],
+                   "traffic": traffic_all.get(k)} for k in alg}
 
+    # ---- the other BASELINE configurations (bounded; never allowed to break the contract line) ----
+    extras = {}
+    if not args.no_extras:
+        import bench_extras as X
+        for key, fn in (("strong", lambda: X.strong_scaling(dev, peaks["tflops"], steps=max(K, 20))),
+                        ("tt_sh25", lambda: X.strong_scaling(dev, peaks["tflops"], steps=max(K, 20), tt=True)),
+                        ("c4_extraction", lambda: X.c4_extraction(dev, peaks["tflops"])),
+                        ("c5_octree_opt", lambda: X.c5_octree_opt(dev))):
+            try:
+                torch.cuda.empty_cache()
+                extras[key] = fn()
+            except Exception as e:   # noqa: BLE001
+                extras[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise   # ranks would desynchronise: fail loudly instead
     if rank == 0:
         value = world * RAYS * K / (ms_total * 1e-3)
         e2e = world * RAYS * K / (ms_e2e * 1e-3)
@@ -371,9 +396,12 @@ def main():
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                          "peak_source": peaks["src"],
-                         "algorithmic_flops_per_step": alg[dom], "share_of_step": per_step_ms[dom] / sum(per_step_ms.values())},
+                         "algorithmic_flops_per_step": alg[dom], "share_of_step": per_step_ms[dom] / sum(per_step_ms.values()),
+                         "step_frac": FLOP_PER_STEP * f_scale / (ms_total / K * 1e-3) / 1e12 / peaks["tflops"],
+                         "kernels": kernels},
             "clocks": sampler.summary() if sampler else None,
         }
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)

@@ -161,20 +161,26 @@ typedef struct pob_train_hparams {
 
 /* grad_flat [num_mlps * pob_param_count] (MLP_0 then MLP_1, reference flat order), per-rank gradient of
  *   mean((rgb_f-px)^2) + mean((rgb_c-px)^2) + sparsity_weight*(1-mean(exp(-len*relu(sigma(p)))))
- * stats [8] (device): [0] sum (rgb_fine-px)^2, [1] sum (rgb_coarse-px)^2, [2] sum exp(-len*relu(sigma)). */
+ * stats [8] (device): [0] sum (rgb_fine-px)^2, [1] sum (rgb_coarse-px)^2, [2] sum exp(-len*relu(sigma)).
+ * The backward of MLP_0 (coarse level) is finished first; mlp0_done_event (a cudaEvent_t, or NULL) is recorded on
+ * `stream` once grad_flat[0 : pob_param_count) is final, so that the caller can all-reduce that bucket on another
+ * stream while the MLP_1 backward (three quarters of the work) is still running (the two branches are independent:
+ * stop_gradient, nerf_sh/nerf/model_utils.py:286). */
 int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp, const void* packed_coarse_dev,
                       const void* packed_fine_dev, const float* origins_dev, const float* directions_dev,
                       const float* viewdirs_dev, const float* pixels_dev, int n_rays, const float* z_base_dev,
                       const float* t_rand_dev, const float* u_dev, int u_per_ray, const float* z_fine_dev,
                       const float* sp_points_dev, float* grad_flat_dev, float* stats_dev, void* workspace_dev,
-                      void* stream);
+                      void* mlp0_done_event, void* stream);
 
 /* flax.optim.Adam (beta1 .9, beta2 .999, eps 1e-8; nerf_sh/nerf/models.py:44) on the flat buffers of
  * num_mlps MLPs, g = grad*grad_mult + weight_decay_coef*param, then re-packs the operand blobs.
- * `step` = number of updates already applied (flax optimizer.state.step). */
+ * `step` = number of updates already applied (flax optimizer.state.step).  lr_step_dev (device float[2] = {lr,
+ * step}, or NULL) overrides the two host values, so that a captured CUDA graph of the step can be replayed with a
+ * new learning rate and step count. */
 int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* grads_dev, float* m_dev,
-                    float* v_dev, float lr, float step, float grad_mult, float weight_decay_coef,
-                    void* packed_coarse_dev, void* packed_fine_dev, void* stream);
+                    float* v_dev, float lr, float step, const float* lr_step_dev, float grad_mult,
+                    float weight_decay_coef, void* packed_coarse_dev, void* packed_fine_dev, void* stream);
 
 /* Profiling aid: pob_eval_points_raw (sigma only, FP16) that also records clock64() stamps of CTA 0 into
  * trace_dev[3][256] (role 0 = MMA issuer, 1/2 = first epilogue warp of tile X/Y); scripts/trace_fwd.py.

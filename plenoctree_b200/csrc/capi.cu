@@ -135,7 +135,7 @@ pob::FwdParams pob_base_params(const void* packed, int sh_deg) { return base_par
 
 extern "C" {
 
-int pob_abi_version(void) { return 3; }   // 3: CTA-pair kernels (tile arrays padded to 4 tiles), pob_debug_bwdw_stalls removed
+int pob_abi_version(void) { return 4; }   // 4: pob_loss_and_grad(mlp0_done_event), pob_adam_update(lr_step_dev); 3: CTA-pair kernels
 
 long long pob_launch_count(void) { return g_launches.load(); }
 

@@ -139,8 +139,9 @@ cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_N
                                 const int role_count[WG_NUM_ROLES], int K, float inv_scale,
                                 float* grad_flat, cudaStream_t stream, const float* partials2 = nullptr);
 // flax.optim.Adam.apply_gradient on a flat buffer; grad is multiplied by grad_mult first
+// lr_step_dev (optional, device [2] = {lr, step}) overrides the host lr / step: a captured graph replays with new values
 cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, long long n, float lr,
-                        float step, float beta1, float beta2, float eps, float grad_mult,
+                        float step, const float* lr_step_dev, float beta1, float beta2, float eps, float grad_mult,
                         float weight_decay_coef, cudaStream_t stream);
 
 // ---- flat parameter layout of one MLP (reference order) -------------------------------------

@@ -709,7 +709,10 @@ int tree_dev(const char* where, const pob_octree* t, TreeDev& T) {
 
 int opts_dev(const char* where, const pob_octree_opts* o, Opts& O) {
   if (!o) return pob_fail(where, "options are NULL");
-  if (!(o->step_size >= 0.f)) return pob_fail(where, "step_size must be >= 0");
+  // every march iteration advances by at least step_size (unit cube): below sqrt(3) / MAX_MARCH_STEPS a diagonal ray
+  // would run into the iteration cap and composite the background through the unmarched remainder
+  if (!(o->step_size >= 1.4e-5f))
+    return pob_fail(where, "step_size must be >= 1.4e-5 (the march is capped at 131072 steps per ray)");
   O.step = o->step_size;
   O.bg = o->background_brightness;
   O.sigma_thresh = o->sigma_thresh;
@@ -873,8 +876,8 @@ int pob_octree_adam_step(float* data_dev, float* grad_dev, float* m_dev, float* 
   if (pob_sm_count_cached() <= 0) return pob_fail(W, "no sm_100 CUDA device (there is no CPU fallback)");
   if (n == 0) return 0;
   pob_count_launch();
-  POB_CUDA(W, pob::launch_adam(data_dev, grad_dev, m_dev, v_dev, n, lr, step, 0.9f, 0.999f, eps, 1.0f, 0.0f,
-                               (cudaStream_t)stream));
+  POB_CUDA(W, pob::launch_adam(data_dev, grad_dev, m_dev, v_dev, n, lr, step, nullptr, 0.9f, 0.999f, eps, 1.0f,
+                               0.0f, (cudaStream_t)stream));
   POB_CUDA(W, cudaMemsetAsync(grad_dev, 0, size_t(n) * sizeof(float), (cudaStream_t)stream));
   return 0;
 }

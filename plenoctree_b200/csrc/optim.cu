@@ -109,10 +109,17 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a) {
 }
 
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float bc1, float bc2, float beta1,
-                            float beta2, float eps, float grad_mult, float wd) {
+                            float* __restrict__ v, long long n, float lr, float bc1, float bc2,
+                            const float* __restrict__ lr_step, float beta1, float beta2, float eps, float grad_mult,
+                            float wd) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (lr_step) {   // learning rate and step count live on the device (replayable CUDA graphs)
+    lr = __ldg(lr_step);
+    const float t = __ldg(lr_step + 1) + 1.0f;
+    bc1 = 1.0f - powf(beta1, t);
+    bc2 = 1.0f - powf(beta2, t);
+  }
   const float p = param[i];
   const float g = grad[i] * grad_mult + wd * p;
   const float mi = (1.0f - beta1) * g + beta1 * m[i];
@@ -145,14 +152,14 @@ cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_N
 }
 
 cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, long long n, float lr,
-                        float step, float beta1, float beta2, float eps, float grad_mult,
+                        float step, const float* lr_step_dev, float beta1, float beta2, float eps, float grad_mult,
                         float weight_decay_coef, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const double t = double(step) + 1.0;
   const float bc1 = float(1.0 - pow(double(beta1), t));
   const float bc2 = float(1.0 - pow(double(beta2), t));
-  adam_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, bc1, bc2, beta1,
-                                                              beta2, eps, grad_mult, weight_decay_coef);
+  adam_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, bc1, bc2, lr_step_dev,
+                                                              beta1, beta2, eps, grad_mult, weight_decay_coef);
   return cudaGetLastError();
 }
 

@@ -208,7 +208,7 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
                       const float* viewdirs_dev, const float* pixels_dev, int n_rays, const float* z_base_dev,
                       const float* t_rand_dev, const float* u_dev, int u_per_ray, const float* z_fine_dev,
                       const float* sp_points_dev, float* grad_flat_dev, float* stats_dev, void* workspace_dev,
-                      void* stream) {
+                      void* mlp0_done_event, void* stream) {
   const char* where = "pob_loss_and_grad";
   if (int e = check_cfg(where, cfg)) return e;
   if (!hp) return pob_fail(where, "hparams is NULL");
@@ -293,15 +293,19 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
   if (Nf > 0) jobs[njobs++] = Job{packed_fine_dev, &F, (long long)n_rays * (Nc + Nf), viewdirs_dev, Nc + Nf, 1};
   if (sparsity) jobs[njobs++] = Job{pk_main, &S, sp_n, sp_points_dev, 0, Nf > 0 ? 1 : 0};
 
-  // ---- dgrad launches, then one wgrad launch per MLP over the saved dZ / h tiles ----
-  for (int j = 0; j < njobs; ++j) {
-    Job& J = jobs[j];
-    BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
-    pob_count_launch();
-    PobPhaseTimer _t(POB_PH_BWD, st);
-    POB_CUDA(where, launch_mlp_bwd(b, sms, st));
-  }
+  // ---- per MLP: dgrad launches of its levels, then ONE wgrad launch over their saved dZ / h tiles ----
+  // MLP_0 (coarse level only) is finished first: its branch of the graph is independent of MLP_1's
+  // (stop_gradient, model_utils.py:286), so the caller can all-reduce the MLP_0 bucket of the gradient
+  // (mlp0_done_event) while the 3x larger MLP_1 backward is still running.
   for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
+    for (int j = 0; j < njobs; ++j) {
+      Job& J = jobs[j];
+      if (J.mlp != mlp) continue;
+      BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
+      pob_count_launch();
+      PobPhaseTimer _t(POB_PH_BWD, st);
+      POB_CUDA(where, launch_mlp_bwd(b, sms, st));
+    }
     WgradParams g;
     memset(&g, 0, sizeof(g));
     Level& L = mlp == 0 ? C : F;
@@ -320,13 +324,14 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     { pob_count_launch(); PobPhaseTimer _t(POB_PH_WGRAD, st); POB_CUDA(where, launch_mlp_wgrad(g, nctas, st)); }
     { pob_count_launch(); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_reduce_grads(w.partials[mlp], rs, rc, K, 1.0f / hp->loss_scale,
                                         grad_flat_dev + size_t(mlp) * P, st)); }
+    if (mlp == 0 && Nf > 0 && mlp0_done_event) POB_CUDA(where, cudaEventRecord((cudaEvent_t)mlp0_done_event, st));
   }
   return 0;
 }
 
 int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* grads_dev, float* m_dev,
-                    float* v_dev, float lr, float step, float grad_mult, float weight_decay_coef,
-                    void* packed_coarse_dev, void* packed_fine_dev, void* stream) {
+                    float* v_dev, float lr, float step, const float* lr_step_dev, float grad_mult,
+                    float weight_decay_coef, void* packed_coarse_dev, void* packed_fine_dev, void* stream) {
   const char* where = "pob_adam_update";
   if (sh_deg < -1 || sh_deg > 4) return pob_fail(where, "sh_deg must be in [-1, 4]");
   if (num_mlps < 1 || num_mlps > 2) return pob_fail(where, "num_mlps must be 1 or 2");
@@ -335,7 +340,7 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
   cudaStream_t st = (cudaStream_t)stream;
   const int K = sh_deg < 0 ? 1 : (sh_deg + 1) * (sh_deg + 1);
   const long long P = flat_layout(K).total;
-  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_adam(params_dev, grads_dev, m_dev, v_dev, P * num_mlps, lr, step, 0.9f, 0.999f, 1e-8f,
+  { pob_count_launch(1); PobPhaseTimer _t(POB_PH_OPTIM, st); POB_CUDA(where, launch_adam(params_dev, grads_dev, m_dev, v_dev, P * num_mlps, lr, step, lr_step_dev, 0.9f, 0.999f, 1e-8f,
                               grad_mult, weight_decay_coef, st)); }
   if (int e = pob_pack_weights(params_dev, sh_deg, packed_coarse_dev, stream)) return e;
   if (num_mlps == 2)

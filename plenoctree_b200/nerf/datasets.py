@@ -27,16 +27,39 @@ class Dataset:
         self.batch_size = int(args.batch_size) // world
         self.image_batching = bool(args.image_batching)
         self._load_renderings(args)
-        rays = generate_rays(self.w, self.h, self.focal, self.camtoworlds)   # [n,h,w,3] x3 (utils.py:545-589)
         self.n_examples = self.images.shape[0]
-        n, hw = self.n_examples, self.h * self.w
-        self.rays_np = rays
-        if split == "train":
-            self.pixels = torch.from_numpy(self.images.reshape(n, hw, 3)).to(self.device)
-            self.rays = Rays(*[torch.from_numpy(np.ascontiguousarray(r.reshape(n, hw, 3))).to(self.device) for r in rays])
-            self.gen = torch.Generator(device=self.device)
-            self.gen.manual_seed(20201473 + rank)            # np.random.seed(20201473 + host_id), train.py:128
+        # Rays are built on first use: the octree CLIs only read camtoworlds / images, and the per-pixel ray set of a
+        # Tanks&Temples scene (1920x1080, hundreds of views) is tens of GB on the host and in HBM.
+        self._rays_np = None
+        self._pool = None
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(20201473 + rank)                # np.random.seed(20201473 + host_id), train.py:128
         self.it = 0
+
+    @property
+    def rays_np(self):
+        """per-pixel Rays of every view, [n,h,w,3] x3 numpy (utils.py:545-589)."""
+        if self._rays_np is None:
+            self._rays_np = generate_rays(self.w, self.h, self.focal, self.camtoworlds)
+        return self._rays_np
+
+    def _device_pool(self):
+        """pixels [n,hw,3] and Rays [n,hw,3] x3 resident in HBM (training batches are gathered on the device)."""
+        if self._pool is None:
+            n, hw = self.n_examples, self.h * self.w
+            pixels = torch.from_numpy(self.images.reshape(n, hw, 3)).to(self.device)
+            rays = Rays(*[torch.from_numpy(np.ascontiguousarray(r.reshape(n, hw, 3))).to(self.device)
+                          for r in self.rays_np])
+            self._pool = (pixels, rays)
+        return self._pool
+
+    @property
+    def pixels(self):
+        return self._device_pool()[0]
+
+    @property
+    def rays(self):
+        return self._device_pool()[1]
 
     def _load_renderings(self, args):
         raise NotImplementedError

@@ -1,8 +1,10 @@
 """train_step of the reference (nerf_sh/train.py:51-121) on the CUDA library.
 
     loss_fn + value_and_grad   -> lib.pob_loss_and_grad   (fused tcgen05 forward / dgrad / wgrad)
-    lax.pmean(grad, "batch")   -> one torch.distributed all-reduce on the flat gradient (NCCL)
+    lax.pmean(grad, "batch")   -> two torch.distributed all-reduces on the flat gradient (NCCL): the MLP_0 bucket
+                                  on a side stream while the MLP_1 backward still runs, then [MLP_1 | stats]
     optimizer.apply_gradient   -> lib.pob_adam_update      (flax Adam + operand re-pack)
+GraphedTrainStep captures the whole step (jitter draws, kernels, collectives, Adam) in one CUDA graph.
 
 Data parallel layout = one process per GPU; `batch` holds this rank's shard of the global batch
 (reference: batch_size is global and split over devices, nerf_sh/nerf/utils.py:518-522, F8).
@@ -41,8 +43,13 @@ class TrainState:
         self.m = torch.zeros_like(model.params)
         self.v = torch.zeros_like(model.params)
         self.step = 0
-        # gradient buffer: [params | 8 stats] so that one all-reduce carries both pmean calls
+        # gradient buffer: [params | 8 stats] so that the last all-reduce carries both pmean calls
         self.gbuf = torch.zeros(model.params.numel() + 8, dtype=torch.float32, device=model.device)
+        # device copy of (lr, step) for replayable graphs, bucket-overlap plumbing (created on first use)
+        self.lr_step = torch.zeros(2, dtype=torch.float32, device=model.device)
+        self.side_stream = None
+        self.ev_mlp0 = None
+        self.ev_bucket0 = None
 
     @property
     def grads(self):
@@ -60,8 +67,9 @@ def default_loss_scale(n_rays):
 
 def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
                   randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None, z_fine=None,
-                  sigma_noise=None):
-    """value_and_grad(loss_fn) for this rank's shard; fills state.grads / state.stats_raw (device)."""
+                  sigma_noise=None, mlp0_event=None):
+    """value_and_grad(loss_fn) for this rank's shard; fills state.grads / state.stats_raw (device).
+    mlp0_event (torch.cuda.Event): recorded on the current stream once the MLP_0 half of the gradient is final."""
     rays = batch["rays"]
     o = _cuda_f32(rays.origins, "rays.origins", 3)
     d = _cuda_f32(rays.directions, "rays.directions", 3)
@@ -86,7 +94,8 @@ def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.0
                                 ptr(model.blobs[1]) if model.num_mlps == 2 else None, ptr(o), ptr(d), ptr(v),
                                 ptr(px), n, ptr(model.z_base), ptr(t_rand), ptr(u), upr,
                                 ptr(z_fine), ptr(sp_points) if use_sp else None, ptr(state.grads),
-                                ptr(state.stats_raw), ptr(ws), stream_ptr()))
+                                ptr(state.stats_raw), ptr(ws),
+                                mlp0_event.cuda_event if mlp0_event is not None else None, stream_ptr()))
     return n
 
 
@@ -101,13 +110,36 @@ def stats_from_raw(raw, n_rays, sparsity_weight, sparsity_npoints, two_level, wo
     return Stats(loss, psnr, loss_c, loss_sp, psnr_c, float("nan"))
 
 
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def allreduce_gradients(gbuf):
     """lax.pmean(grad) + lax.pmean(stats) (nerf_sh/train.py:117-118) as ONE all-reduce(SUM) on the flat
     [grads | stats] buffer; returns the world size whose reciprocal the caller folds into Adam / stats."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    world = _world()
+    if world > 1:
         dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
-        return dist.get_world_size()
-    return 1
+    return world
+
+
+def bucket_overlap_enabled():
+    """POB_BUCKET_OVERLAP=1: all-reduce the MLP_0 half of the gradient on a side stream under the MLP_1 backward.
+    Off by default: the forward / backward kernels are persistent, one CTA (pair) per SM with a static share of
+    the tiles, so the SMs an overlapping NCCL kernel occupies start their share late and the launch ends later by
+    about the time the overlap saved (measured at 2 GPUs: bench_extras `strong`)."""
+    import os
+    return os.environ.get("POB_BUCKET_OVERLAP", "0") not in ("", "0")
+
+
+def _bucket_plumbing(state):
+    if state.side_stream is None:
+        state.side_stream = torch.cuda.Stream(device=state.model.device)
+        state.ev_mlp0 = torch.cuda.Event()
+        state.ev_bucket0 = torch.cuda.Event()
+        state.ev_mlp0.record()          # materialise the cudaEvent_t handles
+        state.ev_bucket0.record()
+    return state.side_stream, state.ev_mlp0, state.ev_bucket0
 
 
 def shard_batch(batch_size, rank, world):
@@ -120,17 +152,35 @@ def shard_batch(batch_size, rank, world):
 
 def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
                weight_decay_mult=0.0, randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None,
-               sync_stats=False):
+               sync_stats=False, lr_step_on_device=False, collective=True):
     """One optimisation step (nerf_sh/train.py:51-121).  Returns Stats when sync_stats (forces a
     device->host read of the six scalars, like the reference's periodic logging), else None."""
-    n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand, u,
-                      sp_points, loss_scale)
-    world = allreduce_gradients(state.gbuf)   # pmean(grad) and pmean(stats) in one bucket
+    world = _world() if collective else 1     # collective=False: single-rank semantics inside a multi-rank job
+    P = model.P
+    if world > 1 and model.num_mlps == 2 and bucket_overlap_enabled():
+        # two buckets: MLP_0's half is all-reduced on a side stream as soon as its backward is done (the event is
+        # recorded inside pob_loss_and_grad), hidden under the MLP_1 backward; [MLP_1 | stats] follows on this stream
+        side, ev_mlp0, ev_b0 = _bucket_plumbing(state)
+        n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand,
+                          u, sp_points, loss_scale, mlp0_event=ev_mlp0)
+        side.wait_event(ev_mlp0)
+        with torch.cuda.stream(side):
+            dist.all_reduce(state.gbuf[:P], op=dist.ReduceOp.SUM)
+            ev_b0.record(side)
+        dist.all_reduce(state.gbuf[P:], op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().wait_event(ev_b0)
+    else:
+        n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand,
+                          u, sp_points, loss_scale)
+        if world > 1:
+            allreduce_gradients(state.gbuf)   # pmean(grad) and pmean(stats) in one bucket
     # weight_l2 = sum(theta^2)/numel  ->  d/dtheta = 2*theta/numel  (train.py:101-108,114)
     wd = 2.0 * weight_decay_mult / model.params.numel() if weight_decay_mult else 0.0
     check(lib.pob_adam_update(model.sh_deg, model.num_mlps, ptr(model.params), ptr(state.grads), ptr(state.m),
-                              ptr(state.v), float(lr), float(state.step), 1.0 / world, wd, ptr(model.blobs[0]),
-                              ptr(model.blobs[1]) if model.num_mlps == 2 else None, stream_ptr()))
+                              ptr(state.v), float(lr), float(state.step),
+                              ptr(state.lr_step) if lr_step_on_device else None, 1.0 / world, wd,
+                              ptr(model.blobs[0]), ptr(model.blobs[1]) if model.num_mlps == 2 else None,
+                              stream_ptr()))
     state.step += 1
     if sync_stats:
         raw = state.stats_raw / world
@@ -139,3 +189,60 @@ def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.
         wl2 = float((model.params.double() ** 2).sum() / model.params.numel())
         return st._replace(weight_l2=wl2)
     return None
+
+
+class GraphedTrainStep:
+    """One train_step captured in a CUDA graph (jitter draws, ~30 kernel launches, both gradient all-reduces, Adam,
+    operand re-pack) and replayed per step: at 512 rays per GPU (BASELINE's global batch of 4096 on 8 GPUs) the
+    launches would otherwise cost as much as the kernels.  The batch lives in static device buffers; the learning
+    rate and the step count reach the Adam kernel through a two-float device buffer written before every replay.
+
+        g = GraphedTrainStep(model, state, n_rays)
+        g.step(batch, lr)            # batch tensors may be host (pinned) or device; copied into the static buffers
+    """
+
+    def __init__(self, model, state, n_rays, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
+                 weight_decay_mult=0.0, warmup=3, collective=True):
+        self.model, self.state, self.n = model, state, int(n_rays)
+        dev = model.device
+        self.buf = torch.zeros((self.n, 12), dtype=torch.float32, device=dev)       # [o | d | v | px]
+        self._host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.kw = dict(sparsity_weight=sparsity_weight, sparsity_length=sparsity_length,
+                       sparsity_radius=sparsity_radius, weight_decay_mult=weight_decay_mult, lr_step_on_device=True,
+                       collective=collective)
+        b = self._batch()
+        # warm-up on a side stream (allocations, NCCL communicator, lazy module loads), then capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        step0 = state.step
+        snap = [t.clone() for t in (model.params, state.m, state.v)]
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._set_hyper(0.0)
+                train_step(model, state, b, 0.0, **self.kw)
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            train_step(model, state, b, 0.0, **self.kw)
+        # the warm-up / capture steps ran with lr = 0 but still moved the Adam moments: restore
+        for t, c in zip((model.params, state.m, state.v), snap):
+            t.copy_(c)
+        model.repack()
+        state.step = step0
+
+    def _batch(self):
+        from .models import Rays
+        b = self.buf
+        return {"rays": Rays(b[:, 0:3], b[:, 3:6], b[:, 6:9]), "pixels": b[:, 9:12]}
+
+    def _set_hyper(self, lr):
+        self._host[0] = float(lr)
+        self._host[1] = float(self.state.step)
+        self.state.lr_step.copy_(self._host, non_blocking=True)
+
+    def step(self, batch12, lr):
+        """batch12: [n_rays, 12] float32 tensor (origins | directions | viewdirs | pixels), host-pinned or device."""
+        self.buf.copy_(batch12, non_blocking=True)
+        self._set_hyper(lr)
+        self.graph.replay()
+        self.state.step += 1

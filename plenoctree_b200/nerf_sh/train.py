@@ -18,14 +18,7 @@ FLAGS = F.FLAGS
 F.define_flags()
 
 
-def _dist_init():
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, torch.device("cuda", local)
+from .._dist import dist_init as _dist_init  # noqa: E402
 
 
 def main(unused_argv):

@@ -76,6 +76,8 @@ def calculate_grid_weights(dataset, sigmas, reso, invradius, offset, step_size=1
     grid = sigmas.reshape(reso, reso, reso).contiguous().float()
     wmax = torch.zeros_like(grid)
     c2ws = np.asarray(dataset.camtoworlds, dtype=np.float32)
+    rank, world = _rank_world()
+    c2ws = c2ws[rank::world]        # cameras are dealt to the ranks; the per-voxel maxima are joined below
     cams = camera_array(c2ws, dataset.w, dataset.h, dataset.focal, device=dev)
     o = _lib.OctreeOpts()
     o.step_size = float(step_size)
@@ -88,6 +90,9 @@ def calculate_grid_weights(dataset, sigmas, reso, invradius, offset, step_size=1
         sub = cams[c0:c0 + cam_chunk].contiguous()
         check(lib.pob_grid_weight_render(ptr(grid), reso, ptr(sub), sub.shape[0], int(dataset.w), int(dataset.h), off,
                                          inv, ctypes.byref(o), ptr(wmax), None, stream_ptr()))
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
     return wmax
 
 
@@ -170,11 +175,13 @@ def step2(args, tree, nerf, cells_per_launch=None):
     n = int(leaf_ind.shape[0])
     out = torch.zeros((n, tree.data_dim), dtype=torch.float32, device=tree.device)
     gen = torch.Generator(device=tree.device)
-    # leaf chunks are dealt round-robin to the ranks (contiguous leaf ranges, no collective inside); each chunk draws
-    # its sample positions from its own seed, so the tree does not depend on the number of ranks
-    for cid, i in enumerate(range(0, n, cells_per_launch)):
-        if cid % world != rank:
-            continue
+    # every rank takes a contiguous block of leaf chunks (no collective inside); each chunk draws its sample
+    # positions from its own seed, so the tree does not depend on the number of ranks.  The blocks are all-gathered.
+    n_chunks = (n + cells_per_launch - 1) // cells_per_launch
+    per_rank = (n_chunks + world - 1) // world
+    c_lo, c_hi = min(n_chunks, rank * per_rank), min(n_chunks, (rank + 1) * per_rank)
+    for cid in range(c_lo, c_hi):
+        i = cid * cells_per_launch
         chunk_inds = leaf_ind[i:i + cells_per_launch]
         gen.manual_seed(20200823 + cid)
         u = torch.rand((chunk_inds.shape[0], S, 3), device=tree.device, generator=gen)
@@ -194,7 +201,13 @@ def step2(args, tree, nerf, cells_per_launch=None):
             rgb_avg[msum[..., 0] < 1e-3] = 0
             out[i:i + cells_per_launch] = torch.cat([rgb_avg, sigma.mean(dim=1)], dim=-1)
     if world > 1:
-        dist.all_reduce(out)          # every row was written by exactly one rank
+        rows = per_rank * cells_per_launch            # rows of one rank's block (the last block may be short)
+        mine = torch.zeros((rows, tree.data_dim), dtype=torch.float32, device=tree.device)
+        lo, hi = min(n, c_lo * cells_per_launch), min(n, c_hi * cells_per_launch)
+        mine[:hi - lo] = out[lo:hi]
+        full = torch.empty((world * rows, tree.data_dim), dtype=torch.float32, device=tree.device)
+        dist.all_gather_into_tensor(full, mine)
+        out = full[:n]
     tree[leaf_ind] = out
 
 
@@ -230,7 +243,7 @@ def extract(args, nerf, dataset):
     step2(args, tree, nerf)
     tree[:, -1:].relu_()
     tree.shrink_to_fit()
-    if args.output:
+    if args.output and _rank_world()[0] == 0:   # the tree is replicated: rank 0 writes it
         tree.save(args.output, compress=False)
     return tree
 
@@ -288,7 +301,8 @@ def main(unused_argv):
     F.update_flags(FLAGS)
     F.check_scope(FLAGS)
     torch.manual_seed(20200823)
-    dev = torch.device("cuda")
+    from .._dist import dist_finish, dist_init
+    rank, _, dev = dist_init()       # under torchrun: NCCL group, this rank's GPU (x-slabs / leaf blocks / cameras)
     nerf = load_nerf(FLAGS, dev)
     assert FLAGS.data_dir  # Dataset is required now (extraction.py:455)
     dataset = datasets.get_dataset("train", FLAGS, device=dev)
@@ -296,12 +310,14 @@ def main(unused_argv):
     if base_dir:
         os.makedirs(base_dir, exist_ok=True)
     tree = extract(FLAGS, nerf, dataset)
-    print(tree)
-    if FLAGS.eval:
-        from .evaluation import eval_octree
-        test = datasets.get_dataset("test", FLAGS, device=dev)
-        psnr, ssim = eval_octree(tree, test, FLAGS)
-        print("Average PSNR", psnr, "SSIM", ssim)
+    if rank == 0:
+        print(tree)
+        if FLAGS.eval:
+            from .evaluation import eval_octree
+            test = datasets.get_dataset("test", FLAGS, device=dev)
+            psnr, ssim = eval_octree(tree, test, FLAGS)
+            print("Average PSNR", psnr, "SSIM", ssim)
+    dist_finish()
     return tree
 
 

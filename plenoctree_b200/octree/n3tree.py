@@ -352,7 +352,7 @@ class N3TreeView:
         tree = self.tree
         corn_unit, depth = tree._corners_unit(self._leaves())
         corn = (corn_unit - tree.offset) / tree.invradius
-        length = torch.exp2(-depth.float() - 1.0)[:, None] / tree.invradius
+        length = torch.pow(float(tree.N), -(depth.float() + 1.0))[:, None] / tree.invradius   # N^-(depth+1)
         if uniforms is None:
             uniforms = torch.rand((corn.shape[0], n_samples, 3), device=tree.device)
         return corn[:, None, :] + uniforms * length[:, None, :]

@@ -7,7 +7,8 @@
     svox.N3Tree.load/save  optimization.py:168,245-248    plenoctree_b200.octree.N3Tree
 
 Multi-GPU: every image's pixel rows are split over the ranks, each rank scatters into its own
-dense gradient buffer, one NCCL all-reduce (SUM) per image joins them before the replicated SGD update.  Both optimiser branches of the reference are fused with zero_grad: SGD (`--sgd`, all shipped configs) and Adam (`--nosgd`).
+dense gradient buffer, and the touched rows are exchanged (exchange_gradients: compacted indices + values, all-gathered)
+before the replicated SGD update.  Both optimiser branches of the reference are fused with zero_grad: SGD (`--sgd`, all shipped configs) and Adam (`--nosgd`).
 """
 import math
 import types
@@ -41,6 +42,48 @@ def row_slab(height, rank, world):
     return r0, base + (1 if rank < rem else 0)
 
 
+def exchange_gradients(tree, sparse=True):
+    """Sum the ranks' gradient buffers before the replicated update.
+
+    dense : one NCCL all-reduce over the whole buffer (n_internal * N^3 * data_dim floats: 160 MB for a 256^3 tree,
+            1.28 GB at 512^3), whatever the image touched.
+    sparse: an image's row slab only reaches the leaves its rays cross, so each rank compacts the rows of its
+            buffer that received a gradient (indices + values), the ranks all-gather those lists (padded to the
+            longest) and add the other ranks' rows into their own buffers.  One host read of the row counts per image.
+    Returns a small dict describing what was exchanged."""
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    if world == 1:
+        return None
+    g = tree.grad_buffer()[:tree.n_internal]
+    if not sparse:
+        dist.all_reduce(g)
+        return {"mode": "dense", "bytes_per_rank": g.numel() * 4}
+    D = g.shape[-1]
+    rows = g.view(-1, D)
+    idx = torch.nonzero((rows != 0).any(dim=1)).squeeze(1)
+    k = torch.tensor([idx.numel()], dtype=torch.int64, device=g.device)
+    ks = torch.empty(world, dtype=torch.int64, device=g.device)
+    dist.all_gather_into_tensor(ks, k)
+    ks = ks.tolist()
+    kmax = max(ks)
+    if kmax == 0:
+        return {"mode": "sparse", "touched_rows": ks, "bytes_per_rank": 0}
+    send_i = torch.zeros(kmax, dtype=torch.int64, device=g.device)
+    send_v = torch.zeros((kmax, D), dtype=g.dtype, device=g.device)
+    send_i[:idx.numel()] = idx
+    send_v[:idx.numel()] = rows[idx]
+    all_i = torch.empty(world * kmax, dtype=torch.int64, device=g.device)
+    all_v = torch.empty((world * kmax, D), dtype=g.dtype, device=g.device)
+    dist.all_gather_into_tensor(all_i, send_i)
+    dist.all_gather_into_tensor(all_v, send_v)
+    for r in range(world):
+        if r != rank and ks[r] > 0:
+            rows.index_add_(0, all_i[r * kmax:r * kmax + ks[r]], all_v[r * kmax:r * kmax + ks[r]])
+    return {"mode": "sparse", "touched_rows": ks, "rows_total": int(rows.shape[0]),
+            "bytes_per_rank": kmax * (D * 4 + 8)}
+
+
 def run_test_step(r, test_c2w, test_gt, H, W, focal):
     """optimization.py:191-209: mean PSNR of full-quality renders (fast=False) over the validation images."""
     tpsnr = 0.0
@@ -61,7 +104,7 @@ def train_epoch(tree, r, train_c2w, train_gt, H, W, focal, lr, adam_eps=None):
     for j, (c2w, im_gt) in enumerate(zip(train_c2w, train_gt)):
         r.train_persp(c2w, im_gt, W, H, focal, rows=rows if world > 1 else None, sq_err=sq[j:j + 1])
         if world > 1:
-            dist.all_reduce(tree.grad_buffer()[:tree.n_internal])
+            exchange_gradients(tree, sparse=True)
         if adam_eps is None:
             tree.sgd_step(lr)
         else:
@@ -78,6 +121,9 @@ def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=prin
     if args.sgd and (args.sgd_momentum != 0.0 or args.sgd_nesterov):
         raise NotImplementedError("SGD momentum is not built (reference configs use momentum 0)")
     H, W = int(train_gt[0].shape[0]), int(train_gt[0].shape[1])
+    rank, _ = _rank_world()
+    if rank != 0:                       # every rank renders / trains the same replicated tree; rank 0 talks and saves
+        log = lambda *a, **k: None      # noqa: E731
     r = VolumeRenderer(tree, step_size=args.renderer_step_size)
     best_validation_psnr = run_test_step(r, test_c2w, test_gt, H, W, focal)
     log(f"** initial val psnr {best_validation_psnr}")
@@ -94,7 +140,7 @@ def optimize(args, tree, train_c2w, train_gt, test_c2w, test_gt, focal, log=prin
             elif not args.continue_on_decrease:
                 log("Stop since overfitting")
                 break
-    if not args.nosave and best_t is not None and args.output:
+    if not args.nosave and best_t is not None and args.output and rank == 0:
         best_t.save(args.output, compress=False)
     return best_t, best_validation_psnr
 
@@ -131,8 +177,8 @@ def main(unused_argv):
         raise NotImplementedError("write_vid (mp4 output) is outside the scope of this path")
     torch.manual_seed(20200823)
     np.random.seed(20200823)
-    dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
+    from .._dist import dist_finish, dist_init
+    _, _, dev = dist_init()          # under torchrun: NCCL group, this rank's GPU (rows of every image are split)
 
     def get_data(stage):
         ds = datasets.get_dataset(stage, FLAGS, device=dev)
@@ -148,7 +194,9 @@ def main(unused_argv):
         test_focal, test_c2w, test_gt = get_data("val")
         assert focal == test_focal
     tree = N3Tree.load(FLAGS.input, map_location=dev)
-    return optimize(FLAGS, tree, train_c2w, train_gt, test_c2w, test_gt, focal)
+    res = optimize(FLAGS, tree, train_c2w, train_gt, test_c2w, test_gt, focal)
+    dist_finish()
+    return res
 
 
 if __name__ == "__main__":

@@ -136,7 +136,7 @@ def test_adam_update_and_repack():
         g = (rs.normal(size=p.shape) * 1e-3).astype(np.float32)
         state.grads.copy_(torch.from_numpy(g))
         check(lib.pob_adam_update(sh_deg, 2, ptr(model.params), ptr(state.grads), ptr(state.m), ptr(state.v),
-                                  5e-4, float(step), 0.5, 0.0, ptr(model.blobs[0]), ptr(model.blobs[1]), None))
+                                  5e-4, float(step), None, 0.5, 0.0, ptr(model.blobs[0]), ptr(model.blobs[1]), None))
         p, m, v = O.adam_step(p, 0.5 * g, m, v, float(step), 5e-4)
     torch.cuda.synchronize()
     np.testing.assert_allclose(model.params.cpu().numpy(), p, rtol=2e-5, atol=1e-7)
