@@ -1,0 +1,8 @@
+"""`python -m nerf_sh.train` (reference README): the same flags and config files, served by plenoctree_b200.nerf_sh.train."""
+import runpy
+
+if __name__ == "__main__":
+    runpy.run_module("plenoctree_b200.nerf_sh.train", run_name="__main__", alter_sys=True)
+else:
+    from plenoctree_b200.nerf_sh.train import *  # noqa: F401,F403
+    from plenoctree_b200.nerf_sh.train import main  # noqa: F401

@@ -12,6 +12,12 @@ What is generated (all fp32, seeds fixed):
   eval_sh.npz      reference nerf_sh/nerf/sh.py::eval_sh for deg 0..4 on random coefficients/dirs.
   posenc.npz       reference octree/nerf/model_utils.py::posenc.
   rays.npz         reference octree/nerf/utils.py::generate_rays on two spherical poses.
+  ref_render.npz   /root/reference/nerf_sh/nerf/model_utils.py and models.py EXECUTED UNMODIFIED over numpy-backed
+                   stand-ins for jax / flax (tests/golden/jax_stub.py): sample_along_rays (plain and with an injected
+                   t_rand), volumetric_rendering, piecewise_constant_pdf (peaky / flat / zero / single-bin weights,
+                   deterministic and injected u), sample_pdf, add_gaussian_noise, the reference MLP class, and the
+                   whole NerfModel.__call__ (64 + 128 samples, SH16, white background, randomized with injected
+                   draws) on oracle-initialised weights.
 """
 import importlib.util
 import os
@@ -165,6 +171,103 @@ def gen_ckpt_bridge():
     print("ckpt_bridge.npz", len(keys), "tensors,", len(blob), "bytes")
 
 
+def gen_ref_render():
+    """Execute the reference's JAX forward path (model_utils.py, models.py::NerfModel.__call__) over numpy."""
+    import types
+    import jax_stub
+    names = jax_stub.install()
+    # nerf_sh.nerf.utils pulls in flax.optim, jax.dlpack, datasets, ...: models.py only needs these two names of it
+    fake_utils = types.ModuleType("nerf_sh.nerf.utils")
+    import collections
+    fake_utils.Rays = collections.namedtuple("Rays", ("origins", "directions", "viewdirs"))
+    fake_utils.TrainState = object
+    sys.modules["nerf_sh.nerf.utils"] = fake_utils
+    try:
+        from nerf_sh.nerf import model_utils as MU
+        from nerf_sh.nerf import models as RM
+        import flax.linen as nn
+        rs = np.random.RandomState(20200823)
+        out = {}
+        B, N, NF = 24, 64, 128
+        poses = np.stack([O.pose_spherical(rs.uniform(-180, 180), rs.uniform(-90, 0), 4.0) for _ in range(4)])
+        rays_all = O.generate_rays(40, 30, 55.5, poses)
+        pick = rs.choice(4 * 30 * 40, B, replace=False)
+        o, d, v = [np.ascontiguousarray(np.asarray(r).reshape(-1, 3)[pick]).astype(np.float32) for r in rays_all]
+        out.update(origins=o, directions=d, viewdirs=v)
+        # ---- sample_along_rays ----
+        t_rand = rs.uniform(size=(B, N)).astype(np.float32)
+        for tag, rnd, lin in (("plain", False, False), ("rand", True, False), ("lindisp_rand", True, True)):
+            z, pts = MU.sample_along_rays(jax_stub.Key(uniform=t_rand), o, d, N, 2.0, 6.0, rnd, lin)
+            out[f"sar_{tag}_z"], out[f"sar_{tag}_pts"] = np.asarray(z), np.asarray(pts)
+        out["t_rand"] = t_rand
+        # ---- volumetric_rendering ----
+        z_sorted = np.sort(rs.uniform(2.0, 6.0, size=(B, N)).astype(np.float32), axis=-1)
+        rgb = rs.uniform(size=(B, N, 3)).astype(np.float32)
+        sigma = (rs.exponential(3.0, size=(B, N, 1)) * (rs.uniform(size=(B, N, 1)) < 0.4)).astype(np.float32)
+        sigma[0] = 0.0                    # an empty ray: the disp guard and the white background take over
+        sigma[1, :, 0] = 80.0             # an opaque one
+        for wb in (True, False):
+            c, di, ac, w = MU.volumetric_rendering(rgb, sigma, z_sorted, d, wb)
+            out[f"vr_rgb_{int(wb)}"], out[f"vr_disp_{int(wb)}"] = np.asarray(c), np.asarray(di)
+            out[f"vr_acc_{int(wb)}"], out[f"vr_weights_{int(wb)}"] = np.asarray(ac), np.asarray(w)
+        out.update(vr_in_rgb=rgb, vr_in_sigma=sigma, vr_in_z=z_sorted)
+        # ---- piecewise_constant_pdf / sample_pdf ----
+        bins = np.sort(rs.uniform(2.0, 6.0, size=(5, N - 1)).astype(np.float32), axis=-1)
+        wts = rs.uniform(size=(5, N - 2)).astype(np.float32)
+        wts[0] = wts[0] ** 8                           # peaky
+        wts[1] = 0.37                                  # flat
+        wts[2] = 0.0                                   # all zero: the eps padding decides
+        wts[3] = 0.0
+        wts[3, 17] = 1.0                               # a single bin
+        u = rs.uniform(size=(5, NF)).astype(np.float32)
+        u[4, :3] = (0.0, np.float32(1.0) - np.finfo(np.float32).eps, 0.5)
+        out.update(pdf_bins=bins, pdf_weights=wts, pdf_u=u)
+        out["pdf_det"] = np.asarray(MU.piecewise_constant_pdf(jax_stub.Key(), bins, wts.copy(), NF, False))
+        out["pdf_rand"] = np.asarray(MU.piecewise_constant_pdf(jax_stub.Key(uniform=u), bins, wts.copy(), NF, True))
+        zc = np.sort(rs.uniform(2.0, 6.0, size=(5, N)).astype(np.float32), axis=-1)
+        zs, ps = MU.sample_pdf(jax_stub.Key(uniform=u), bins, wts.copy(), o[:5], d[:5], zc, NF, True)
+        out.update(spdf_z_coarse=zc, spdf_z=np.asarray(zs), spdf_pts=np.asarray(ps))
+        # ---- add_gaussian_noise ----
+        raw = rs.normal(size=(B, N, 1)).astype(np.float32)
+        nz = rs.normal(size=(B, N, 1)).astype(np.float32)
+        out.update(noise_raw=raw, noise_draw=nz,
+                   noise_on=np.asarray(MU.add_gaussian_noise(jax_stub.Key(normal=nz), raw, 0.7, True)),
+                   noise_off_std=np.asarray(MU.add_gaussian_noise(jax_stub.Key(normal=nz), raw, None, True)),
+                   noise_off_rand=np.asarray(MU.add_gaussian_noise(jax_stub.Key(normal=nz), raw, 0.7, False)))
+        # ---- the reference MLP class and NerfModel.__call__ ----
+        sh_deg = 3
+        flat_c = O.init_flat_params(sh_deg, 5101, bias_scale=0.05)
+        flat_f = O.init_flat_params(sh_deg, 5102, bias_scale=0.05)
+
+        def plist(flat):
+            return [(w.numpy(), b.numpy()) for w, b in O.unflatten(flat, sh_deg)]
+        model = RM.NerfModel(num_coarse_samples=N, num_fine_samples=NF, use_viewdirs=False, sh_deg=sh_deg, sg_dim=-1,
+                             near=2.0, far=6.0, noise_std=None, net_depth=8, net_width=256, net_depth_condition=1,
+                             net_width_condition=128, net_activation=nn.relu, skip_layer=4, num_rgb_channels=48,
+                             num_sigma_channels=1, white_bkgd=True, min_deg_point=0, max_deg_point=10, deg_view=4,
+                             lindisp=False, rgb_activation=nn.sigmoid, sigma_activation=nn.relu,
+                             legacy_posenc_order=False)
+        model.MLP_0._params = plist(flat_c)
+        model.MLP_1._params = plist(flat_f)
+        enc = np.asarray(MU.posenc(rs.uniform(-1.5, 1.5, size=(3, 7, 3)).astype(np.float32), 0, 10))
+        raw_rgb, raw_sigma = model.MLP_1(enc)
+        out.update(mlp_enc=enc, mlp_raw_rgb=np.asarray(raw_rgb), mlp_raw_sigma=np.asarray(raw_sigma))
+        u_f = rs.uniform(size=(B, NF)).astype(np.float32)
+        for tag, rnd in (("det", False), ("rand", True)):
+            ret = model(jax_stub.Key(uniform=t_rand), jax_stub.Key(uniform=u_f), fake_utils.Rays(o, d, v), rnd)
+            for lvl, (c, di, ac) in zip(("coarse", "fine"), ret):
+                out[f"call_{tag}_{lvl}_rgb"], out[f"call_{tag}_{lvl}_disp"] = np.asarray(c), np.asarray(di)
+                out[f"call_{tag}_{lvl}_acc"] = np.asarray(ac)
+        out.update(call_u=u_f, seeds=np.array([5101, 5102]), sh_deg=sh_deg)
+    finally:
+        jax_stub.uninstall(names)
+        for k in [k for k in sys.modules if k.startswith("nerf_sh")]:
+            sys.modules.pop(k, None)
+    assert all(np.asarray(a).dtype != np.float64 for a in out.values()), "float64 leaked through the jnp stand-in"
+    np.savez_compressed(os.path.join(HERE, "ref_render.npz"), **out)
+    print("ref_render.npz", len(out), "arrays")
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -201,6 +304,11 @@ def gen_flags():
 if __name__ == "__main__":
     torch.manual_seed(20200823)
     torch.set_num_threads(8)
+    sys.path.insert(0, HERE)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_render":
+        gen_ref_render()
+        sys.exit(0)
+    gen_ref_render()
     gen_eval_points(3, 2048, 20200823, "eval_points_sh16.npz")
     gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
     gen_eval_sh()

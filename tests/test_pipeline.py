@@ -224,3 +224,30 @@ def test_flag_tables_match_the_reference(golden_dir):
         assert set(table) == set(ref[key]), (mod, set(table) ^ set(ref[key]))
         for name, (kind, default) in ref[key].items():
             assert table[name][0] == kind_of(kind) and table[name][1] == default, (mod, name)
+
+
+def test_reference_module_paths_and_yaml(tmp_path):
+    """README.md:58-67,120-135 call `python -m nerf_sh.train --config nerf_sh/config/blender ...` and
+    `python -m octree.extraction ...`: the top-level shims resolve to this package's CLIs and a config file with the
+    reference's keys (nerf_sh/config/blender.yaml) overrides the flags (YAML > command line, utils.py:233-244)."""
+    import subprocess
+    import sys
+    cfg = tmp_path / "blender.yaml"
+    cfg.write_text("dataset: blender\nimage_batching: false\nfactor: 0\nnum_coarse_samples: 64\n"
+                   "num_fine_samples: 128\nuse_viewdirs: false\nwhite_bkgd: true\nbatch_size: 1024\nsh_deg: 3\n"
+                   "randomized: true\nmax_steps: 2000000\n")
+    code = (
+        "import sys\n"
+        "from absl import flags\n"
+        "import nerf_sh.train as T, nerf_sh.eval, octree.extraction, octree.optimization, octree.evaluation\n"
+        "from plenoctree_b200.nerf import flags as F\n"
+        "assert T.main.__module__ == 'plenoctree_b200.nerf_sh.train'\n"
+        f"flags.FLAGS(['prog', '--train_dir', '/tmp/x', '--data_dir', '/tmp/y', '--config', r'{cfg.with_suffix('')}', "
+        "'--sh_deg', '1', '--batch_size', '4096'])\n"
+        "F.update_flags(flags.FLAGS)\n"
+        "F.check_flags(flags.FLAGS)\n"
+        "print(flags.FLAGS.sh_deg, flags.FLAGS.batch_size, flags.FLAGS.num_fine_samples, flags.FLAGS.max_steps)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split()[-4:] == ["3", "1024", "128", "2000000"], r.stdout    # the YAML wins over the command line

@@ -140,6 +140,19 @@ def test_adam_update_and_repack():
         p, m, v = O.adam_step(p, 0.5 * g, m, v, float(step), 5e-4)
     torch.cuda.synchronize()
     np.testing.assert_allclose(model.params.cpu().numpy(), p, rtol=2e-5, atol=1e-7)
+    # weight decay (train.py:101-114: loss += weight_decay_mult * sum(theta^2)/numel): g += coef * theta with
+    # coef = 2 * weight_decay_mult / numel, here a large value so that the term matters; lr / step from the device
+    coef = 0.25
+    for step in range(3, 5):
+        g = (rs.normal(size=p.shape) * 1e-3).astype(np.float32)
+        state.grads.copy_(torch.from_numpy(g))
+        state.lr_step.copy_(torch.tensor([3e-4, float(step)]))
+        check(lib.pob_adam_update(sh_deg, 2, ptr(model.params), ptr(state.grads), ptr(state.m), ptr(state.v),
+                                  123.0, -7.0, ptr(state.lr_step), 0.5, coef, ptr(model.blobs[0]),
+                                  ptr(model.blobs[1]), None))
+        p, m, v = O.adam_step(p, 0.5 * g + np.float32(coef) * p, m, v, float(step), 3e-4)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(model.params.cpu().numpy(), p, rtol=2e-5, atol=1e-7)
     # the packed blob follows the new parameters
     from plenoctree_b200 import ops
     pts = torch.from_numpy(rs.uniform(-1, 1, size=(300, 3)).astype(np.float32)).cuda()
