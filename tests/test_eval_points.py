@@ -16,10 +16,13 @@ OUT = os.path.join(ROOT, "gpurun_out")
 # Tolerances (relative to the largest reference magnitude of the compared tensor).
 #   FP16X3: error-compensated operands, fp32-class accuracy -> 1e-4 (north-star bar is 1e-3)
 #   FP16  : 10-bit-mantissa operands (TF32-class, like the reference's default-precision XLA GPU
-#           path), fp32 accumulate -> 1e-2 elementwise on raw pre-activation outputs; the rendered
-#           RGB bar (1e-3) is checked in test_render.py.
+#           path), fp32 accumulate -> the north-star bar itself, 1e-3 of the largest magnitude, elementwise on the
+#           raw pre-activation outputs (measured max 5.5e-4 .. 8.5e-4, profiles/r2_parity_eval_points.json).
+#           On arbitrary random points (no golden vectors; thousands of points, every SH degree) the largest single
+#           error of the 10-layer fp16 chain reaches ~2e-3: those tests use TOL_FP16_ANY.
 TOL_X3 = 1e-4
-TOL_FP16 = 1e-2
+TOL_FP16 = 1e-3
+TOL_FP16_ANY = 3e-3
 
 
 def _record(name, payload):
@@ -95,7 +98,7 @@ def test_ragged_sizes_and_sigma_only(m):
     pts_np = rs.uniform(-1.5, 1.5, size=(m, 3)).astype(np.float32)
     pts = torch.from_numpy(pts_np).cuda()
     guard = torch.full((m + 64, 48), 7.0, device="cuda")  # detect out-of-bounds row writes
-    for prec, tol in ((ops.PREC_FP16X3, TOL_X3), (ops.PREC_FP16, TOL_FP16)):
+    for prec, tol in ((ops.PREC_FP16X3, TOL_X3), (ops.PREC_FP16, TOL_FP16_ANY)):
         rgb, sig = ops.eval_points_raw(blob, sh_deg, pts, precision=prec)
         _, sig_only = ops.eval_points_raw(blob, sh_deg, pts, want_rgb=False, precision=prec)
         torch.cuda.synchronize()
@@ -134,7 +137,7 @@ def test_eval_points_rgb_sigma_all_degrees(sh_deg):
         raw_rgb, raw_sig = O.eval_points_raw(O.unflatten(flat, sh_deg), torch.from_numpy(pts))
         rgb_o = torch.sigmoid(O.eval_sh(sh_deg, raw_rgb.reshape(m, 3, K), torch.from_numpy(vd)))
         sig_o = torch.relu(raw_sig)
-    for prec, tol in ((ops.PREC_FP16X3, TOL_X3), (ops.PREC_FP16, TOL_FP16)):
+    for prec, tol in ((ops.PREC_FP16X3, TOL_X3), (ops.PREC_FP16, TOL_FP16_ANY)):
         rgb, sig = ops.eval_points(blob, sh_deg, torch.from_numpy(pts).cuda(), torch.from_numpy(vd).cuda(),
                                    precision=prec)
         torch.cuda.synchronize()
