@@ -236,6 +236,7 @@ int pob_debug_trace_bwd(const void* packed_dev, int sh_deg, int64_t m, const flo
   b.G = reinterpret_cast<const float4*>(g_dev);
   b.viewdirs = viewdirs_dev;
   b.n_per_ray = 0;
+  b.M_rays = m;
   b.w = base.w;
   b.sh_deg = sh_deg;
   b.K = base.K;

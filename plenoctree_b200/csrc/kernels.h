@@ -25,6 +25,10 @@ struct FwdParams {
   const float* directions;     //             [R,3]
   const float* zvals;          //             [R, n_per_ray]
   int n_per_ray;
+  // SRC_RAYS may carry `M - M_rays` free points behind the ray samples (the sparsity-loss points of the training
+  // step ride on the main level's launches instead of three 40-CTA launches of their own): rows [M_rays, M)
+  long long M_rays;            // SRC_RAYS: R * n_per_ray (== M when there are no extra points)
+  const float* extra_points;   // [M - M_rays, 3]
   const float* viewdirs;       // OUT_RGBS: [R,3] (SRC_RAYS) or [M,3] (SRC_POINTS)
   const float* sigma_noise;    // OUT_RGBS, optional [M]: added to raw sigma before relu (model_utils.py:317-332)
   // SRC_GRID: voxel centres ((i + 0.5)/reso - offset)/scale, x-major flattening (ix,iy,iz)
@@ -95,7 +99,8 @@ cudaError_t launch_composite_bwd(const float4* rgbs, const float* z, const float
                                  float gscale, float4* G, float* sq_err_sum, cudaStream_t st);
 cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const float* u, int u_per_ray, int R,
                               int Nc, int Nf, float* z_out, cudaStream_t st);
-cudaError_t launch_sparsity_grad(const float* sigma_raw, int n, float length, float coef, float4* G,
+// rgbs[i].w = relu(sigma) of the sparsity points (as the OUT_RGBS epilogue leaves it); G[i] = (0,0,0, dL/dsigma_raw)
+cudaError_t launch_sparsity_grad(const float4* rgbs, int n, float length, float coef, float4* G,
                                  float* exp_sum, cudaStream_t st);
 
 // ---- mlp_bwd.cu -----------------------------------------------------------------------------
@@ -104,6 +109,7 @@ struct BwdParams {
   const float4* G;          // [M] (d pre_r, d pre_g, d pre_b, d sigma_raw), loss-scaled
   const float* viewdirs;    // [R,3] (n_per_ray > 0) or [M,3] (n_per_ray == 0)
   int n_per_ray;
+  long long M_rays;         // rows [M_rays, M) are free points (sigma gradient only): no view direction
   MlpPacked w;
   int sh_deg, K, NH;
   const uint32_t* mask;     // [8][Mpad][8] from mlp_fwd

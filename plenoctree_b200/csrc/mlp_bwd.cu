@@ -286,7 +286,7 @@ __device__ __forceinline__ void bwd_body(const BwdParams& p, uint8_t* smem) {
       gq_n = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s_ < p.M) {
         gq_n = p.G[s_];
-        const long long vi = p.n_per_ray > 0 ? s_ / p.n_per_ray : s_;
+        const long long vi = p.n_per_ray > 0 ? (s_ < p.M_rays ? s_ / p.n_per_ray : 0) : s_;   // free points: rgb gradient is 0
         const float* vd = p.viewdirs + 3 * vi;
         vd_n[0] = __ldg(vd); vd_n[1] = __ldg(vd + 1); vd_n[2] = __ldg(vd + 2);
       }

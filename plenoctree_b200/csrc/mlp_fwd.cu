@@ -81,6 +81,11 @@ __device__ __noinline__ void load_point(const FwdParams& p, long long s, float& 
     x = __ldg(q);
     y = __ldg(q + 1);
     z = __ldg(q + 2);
+  } else if (p.src_mode == SRC_RAYS && s >= p.M_rays) {
+    const float* q = p.extra_points + 3 * (s - p.M_rays);   // free points riding behind the ray samples
+    x = __ldg(q);
+    y = __ldg(q + 1);
+    z = __ldg(q + 2);
   } else if (p.src_mode == SRC_RAYS) {
     long long r = s / p.n_per_ray;
     float t = __ldg(p.zvals + s);
@@ -586,7 +591,7 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
 
         if (OUTM == OUT_RGBS) {
           long long sc = s < p.M ? s : p.M - 1;
-          long long vi = (p.src_mode == SRC_RAYS) ? sc / p.n_per_ray : sc;
+          long long vi = (p.src_mode == SRC_RAYS) ? (sc < p.M_rays ? sc / p.n_per_ray : 0) : sc;   // free points: any direction
           const float* vd = p.viewdirs + 3 * vi;
           if (p.sh_deg >= 0) sh_basis(p.sh_deg, __ldg(vd), __ldg(vd + 1), __ldg(vd + 2), basis);
           else basis[0] = 1.f;
@@ -624,7 +629,8 @@ __device__ __forceinline__ void fwd_body(const FwdParams& p, uint8_t* smem) {
             o.x = 1.f / (1.f + expf(-pre[0]));
             o.y = 1.f / (1.f + expf(-pre[1]));
             o.z = 1.f / (1.f + expf(-pre[2]));
-            if (p.sigma_noise != nullptr) sigma_raw += __ldg(p.sigma_noise + s);  // add_gaussian_noise
+            if (p.sigma_noise != nullptr && (p.src_mode != SRC_RAYS || s < p.M_rays))
+              sigma_raw += __ldg(p.sigma_noise + s);  // add_gaussian_noise
             o.w = fmaxf(sigma_raw, 0.f);
             p.out_rgbs[s] = o;
           }

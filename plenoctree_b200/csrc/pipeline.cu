@@ -27,13 +27,12 @@ struct Level {
   float* disp;        // [R]
   float* acc;         // [R]
   float4* G;          // [M]
-  float* sigma;       // [M] (sparsity level only)
   uint8_t *H, *E, *DZ, *DO;
   uint32_t* mask;
 };
 
 struct Workspace {
-  Level lv[3];        // coarse, fine, sparsity
+  Level lv[2];        // coarse, fine; in training the LAST level also carries the sparsity points behind its rays
   float* partials[2]; // wgrad partials of the two MLPs' launches
   size_t total;
 };
@@ -54,23 +53,20 @@ Workspace carve(const pob_render_config& c, int training, uint8_t* base) {
     return p;
   };
   const long long R = c.max_rays;
-  const int Ns[3] = {c.num_coarse_samples, c.num_fine_samples > 0 ? c.num_coarse_samples + c.num_fine_samples : 0,
-                     0};
-  for (int l = 0; l < 3; ++l) {
+  const int Ns[2] = {c.num_coarse_samples, c.num_fine_samples > 0 ? c.num_coarse_samples + c.num_fine_samples : 0};
+  const int last = c.num_fine_samples > 0 ? 1 : 0;
+  for (int l = 0; l < 2; ++l) {
     Level& L = w.lv[l];
-    L.M = (l < 2) ? R * Ns[l] : (training ? c.sparsity_npoints : 0);
+    const long long Mr = R * Ns[l];                                    // ray samples
+    L.M = Mr + ((training && l == last) ? c.sparsity_npoints : 0);     // + sparsity points (train.py:77-83)
     L.tiles = tiles_for(L.M);
-    if (L.M == 0) continue;
-    if (l < 2) {
-      L.z = (float*)take(sizeof(float) * L.M);
-      L.rgbs = (float4*)take(sizeof(float4) * L.M);
-      L.weights = (float*)take(sizeof(float) * L.M);
-      L.comp = (float*)take(sizeof(float) * 3 * R);
-      L.disp = (float*)take(sizeof(float) * R);
-      L.acc = (float*)take(sizeof(float) * R);
-    } else {
-      L.sigma = (float*)take(sizeof(float) * L.M);
-    }
+    if (Mr == 0) continue;
+    L.z = (float*)take(sizeof(float) * Mr);
+    L.rgbs = (float4*)take(sizeof(float4) * L.M);
+    L.weights = (float*)take(sizeof(float) * Mr);
+    L.comp = (float*)take(sizeof(float) * 3 * R);
+    L.disp = (float*)take(sizeof(float) * R);
+    L.acc = (float*)take(sizeof(float) * R);
     if (training) {
       L.G = (float4*)take(sizeof(float4) * L.M);
       L.H = take(size_t(L.tiles) * NUM_TRUNK * A_TILE_BYTES);
@@ -104,6 +100,7 @@ FwdParams ray_fwd_params(const void* packed, int sh_deg, const float* o, const f
   FwdParams p = pob_base_params(packed, sh_deg);
   p.src_mode = SRC_RAYS;
   p.M = (long long)R * N;
+  p.M_rays = p.M;
   p.origins = o;
   p.directions = d;
   p.viewdirs = v;
@@ -118,7 +115,8 @@ FwdParams ray_fwd_params(const void* packed, int sh_deg, const float* o, const f
 int forward_levels(const char* where, const pob_render_config& c, Workspace& w, const void* pk_c,
                    const void* pk_f, const float* o, const float* d, const float* v, int R,
                    const float* z_base, const float* t_rand, const float* u, int u_per_ray,
-                   const float* z_fine, int precision, bool save, cudaStream_t st) {
+                   const float* z_fine, int precision, bool save, cudaStream_t st,
+                   const float* sp_points = nullptr, long long sp_n = 0) {
   const int sms = pob_sm_count_cached();
   const int Nc = c.num_coarse_samples, Nf = c.num_fine_samples;
   Level& C = w.lv[0];
@@ -126,6 +124,10 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
   {
     FwdParams p = ray_fwd_params(pk_c, c.sh_deg, o, d, v, C.z, R, Nc, C.rgbs);
     p.sigma_noise = c.sigma_noise_coarse_dev;
+    if (Nf == 0 && sp_n > 0) {     // single-level model: the sparsity points ride on this launch
+      p.M += sp_n;
+      p.extra_points = sp_points;
+    }
     if (save) {
       p.save_h = C.H;
       p.save_e = C.E;
@@ -143,6 +145,10 @@ int forward_levels(const char* where, const pob_render_config& c, Workspace& w, 
       { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sample_pdf(C.z, C.weights, u, u_per_ray, R, Nc, Nf, F.z, st)); }
     FwdParams p = ray_fwd_params(pk_f, c.sh_deg, o, d, v, F.z, R, Nc + Nf, F.rgbs);
     p.sigma_noise = c.sigma_noise_fine_dev;
+    if (sp_n > 0) {                // the sparsity points ride behind the fine level's ray samples (same MLP)
+      p.M += sp_n;
+      p.extra_points = sp_points;
+    }
     if (save) {
       p.save_h = F.H;
       p.save_e = F.E;
@@ -229,46 +235,46 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
   const int P = flat_layout(K).total;
   Workspace w = carve(*cfg, 1, (uint8_t*)workspace_dev);
   POB_CUDA(where, cudaMemsetAsync(stats_dev, 0, 8 * sizeof(float), st));
+  // The sparsity points (train.py:77-83: eval_points_raw of the fine MLP on uniform points) ride behind the ray
+  // samples of the last level: same MLP, same launches, rows [n_rays * N, n_rays * N + sp_n) of its arrays.
+  const long long sp_n = sparsity ? cfg->sparsity_npoints : 0;
   if (int e = forward_levels(where, *cfg, w, packed_coarse_dev, packed_fine_dev, origins_dev, directions_dev,
                              viewdirs_dev, n_rays, z_base_dev, t_rand_dev, u_dev, u_per_ray, z_fine_dev,
-                             POB_PREC_FP16, true, st))
+                             POB_PREC_FP16, true, st, sp_points_dev, sp_n))
     return e;
   const float gscale = hp->loss_scale * 2.0f / (3.0f * float(n_rays));
   Level& C = w.lv[0];
   Level& F = w.lv[1];
-  Level& S = w.lv[2];
-  const void* pk_main = Nf > 0 ? packed_fine_dev : packed_coarse_dev;  // MLP used by eval_points_raw
+  Level& LAST = Nf > 0 ? F : C;
+  const long long Mr_last = (long long)n_rays * (Nf > 0 ? Nc + Nf : Nc);
   // ---- upstream gradients ----
   { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_bwd(C.rgbs, C.z, directions_dev, C.comp, pixels_dev, n_rays, Nc,
                                        cfg->white_bkgd, gscale, C.G, stats_dev + (Nf > 0 ? 1 : 0), st)); }
   if (Nf > 0)
     { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_composite_bwd(F.rgbs, F.z, directions_dev, F.comp, pixels_dev, n_rays, Nc + Nf,
                                          cfg->white_bkgd, gscale, F.G, stats_dev + 0, st)); }
-  long long sp_n = 0;
   if (sparsity) {
-    sp_n = cfg->sparsity_npoints;
-    FwdParams p = pob_base_params(pk_main, cfg->sh_deg);
-    p.src_mode = SRC_POINTS;
-    p.M = sp_n;
-    p.points = sp_points_dev;
-    p.out_mode = OUT_SIGMA;
-    p.out_sigma = S.sigma;
-    p.save_h = S.H;
-    p.save_e = S.E;
-    p.save_mask = S.mask;
-    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_FWD, st); POB_CUDA(where, launch_mlp_fwd(p, POB_PREC_FP16, false, sms, st)); }
     const float coef = hp->loss_scale * hp->sparsity_weight * hp->sparsity_length / float(sp_n);
-    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sparsity_grad(S.sigma, int(sp_n), hp->sparsity_length, coef, S.G, stats_dev + 2, st)); }
+    { pob_count_launch(1); PobPhaseTimer _t(POB_PH_RENDER, st); POB_CUDA(where, launch_sparsity_grad(LAST.rgbs + Mr_last, int(sp_n), hp->sparsity_length, coef,
+                                                                                                    LAST.G + Mr_last, stats_dev + 2, st)); }
   }
-  // ---- backward ----
+  // ---- backward: per MLP one dgrad launch, then ONE wgrad launch over its saved dZ / h tiles ----
+  // MLP_0 (coarse level only) is finished first: its branch of the graph is independent of MLP_1's
+  // (stop_gradient, model_utils.py:286), so the caller can all-reduce the MLP_0 bucket of the gradient
+  // (mlp0_done_event) while the 3x larger MLP_1 backward is still running.
   const int NH = heads_width(K);
-  auto make_bwd = [&](const void* pk, Level& L, long long M, const float* vd, int npr) {
+  for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
+    Level& L = mlp == 0 ? C : F;
+    const long long Mr = (long long)n_rays * (mlp == 0 ? Nc : Nc + Nf);
+    const long long Mm = Mr + (&L == &LAST ? sp_n : 0);
+    const void* pk = mlp == 0 ? packed_coarse_dev : packed_fine_dev;
     BwdParams b;
     memset(&b, 0, sizeof(b));
-    b.M = M;
+    b.M = Mm;
+    b.M_rays = Mr;
     b.G = L.G;
-    b.viewdirs = vd;
-    b.n_per_ray = npr;
+    b.viewdirs = viewdirs_dev;
+    b.n_per_ray = mlp == 0 ? Nc : Nc + Nf;
     FwdParams base = pob_base_params(pk, cfg->sh_deg);
     b.w = base.w;
     b.sh_deg = cfg->sh_deg;
@@ -277,46 +283,11 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     b.mask = L.mask;
     b.save_dz = L.DZ;
     b.save_do = L.DO;
-    return b;
-  };
-  struct Job {
-    const void* pk;
-    Level* L;
-    long long M;
-    const float* vd;
-    int npr;
-    int mlp;
-  };
-  Job jobs[3];
-  int njobs = 0;
-  jobs[njobs++] = Job{packed_coarse_dev, &C, (long long)n_rays * Nc, viewdirs_dev, Nc, 0};
-  if (Nf > 0) jobs[njobs++] = Job{packed_fine_dev, &F, (long long)n_rays * (Nc + Nf), viewdirs_dev, Nc + Nf, 1};
-  if (sparsity) jobs[njobs++] = Job{pk_main, &S, sp_n, sp_points_dev, 0, Nf > 0 ? 1 : 0};
-
-  // ---- per MLP: dgrad launches of its levels, then ONE wgrad launch over their saved dZ / h tiles ----
-  // MLP_0 (coarse level only) is finished first: its branch of the graph is independent of MLP_1's
-  // (stop_gradient, model_utils.py:286), so the caller can all-reduce the MLP_0 bucket of the gradient
-  // (mlp0_done_event) while the 3x larger MLP_1 backward is still running.
-  for (int mlp = 0; mlp < (Nf > 0 ? 2 : 1); ++mlp) {
-    for (int j = 0; j < njobs; ++j) {
-      Job& J = jobs[j];
-      if (J.mlp != mlp) continue;
-      BwdParams b = make_bwd(J.pk, *J.L, J.M, J.vd, J.npr);
-      pob_count_launch();
-      PobPhaseTimer _t(POB_PH_BWD, st);
-      POB_CUDA(where, launch_mlp_bwd(b, sms, st));
-    }
+    { pob_count_launch(); PobPhaseTimer _t(POB_PH_BWD, st); POB_CUDA(where, launch_mlp_bwd(b, sms, st)); }
     WgradParams g;
     memset(&g, 0, sizeof(g));
-    Level& L = mlp == 0 ? C : F;
-    const long long Mm = (long long)n_rays * (mlp == 0 ? Nc : Nc + Nf);
     g.seg[0] = WgradSegment{L.H, L.DZ, L.E, L.DO};
     g.seg_tiles[0] = tiles_for(Mm);
-    const bool with_sp = sparsity && ((Nf > 0) ? mlp == 1 : mlp == 0);
-    if (with_sp) {
-      g.seg[1] = WgradSegment{S.H, S.DZ, S.E, S.DO};
-      g.seg_tiles[1] = tiles_for(sp_n);
-    }
     g.NH = NH;
     g.partials = w.partials[mlp];
     int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];

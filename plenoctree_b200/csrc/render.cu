@@ -345,14 +345,15 @@ __global__ void __launch_bounds__(RAYS_PER_BLOCK * 32) sample_pdf_kernel(const P
   for (int i = lane; i < Nc + Nf; i += 32) zo[i] = sb[i];
 }
 
-// sparsity-loss gradient (nerf_sh/train.py:77-83): G.w = coef * exp(-len * relu(s)) * [s > 0]
-__global__ void sparsity_grad_kernel(const float* __restrict__ sigma_raw, int n, float length, float coef,
+// sparsity-loss gradient (nerf_sh/train.py:77-83): G.w = coef * exp(-len * relu(s)) * [s > 0]; the forward
+// epilogue has already applied the relu (rgbs.w)
+__global__ void sparsity_grad_kernel(const float4* __restrict__ rgbs, int n, float length, float coef,
                                      float4* __restrict__ G, float* __restrict__ exp_sum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float e = 0.f;
   if (i < n) {
-    const float s = sigma_raw[i];
-    e = expf(-length * fmaxf(s, 0.f));
+    const float s = rgbs[i].w;
+    e = expf(-length * s);
     G[i] = make_float4(0.f, 0.f, 0.f, s > 0.f ? coef * e : 0.f);
   }
   e = warp_sum(e);
@@ -419,10 +420,10 @@ cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const floa
   return cudaGetLastError();
 }
 
-cudaError_t launch_sparsity_grad(const float* sigma_raw, int n, float length, float coef, float4* G,
+cudaError_t launch_sparsity_grad(const float4* rgbs, int n, float length, float coef, float4* G,
                                  float* exp_sum, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  sparsity_grad_kernel<<<(n + 255) / 256, 256, 0, st>>>(sigma_raw, n, length, coef, G, exp_sum);
+  sparsity_grad_kernel<<<(n + 255) / 256, 256, 0, st>>>(rgbs, n, length, coef, G, exp_sum);
   return cudaGetLastError();
 }
 
