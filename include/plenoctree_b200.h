@@ -99,6 +99,14 @@ int pob_eval_points_raw_host(const void* packed_dev, int sh_deg, const float* po
  * expression; t_rand [n_rays,n_samples] in [0,1) replaces random.uniform (NULL = randomized False). */
 int pob_sample_coarse(const float* z_base_dev, const float* t_rand_dev, int n_rays, int n_samples,
                       float* z_out_dev, void* stream);
+
+/* The random draws of one randomized training step in ONE launch (replaces jax.random.uniform at
+ * nerf_sh/nerf/model_utils.py:137 (t_rand [n_t] ~ U[0,1)), :262 (u [n_u] ~ U[0,1)) and nerf_sh/train.py:79
+ * (sp_points [n_sp] ~ U[-radius, radius))): Philox4x32-10 keyed by `seed`, counter = (index, stream, step).  The
+ * threefry streams of the reference cannot be reproduced without JAX; parity tests inject their own draws.
+ * step_dev (device float, or NULL) overrides `step`, so that a replayed CUDA graph draws fresh numbers. */
+int pob_draw_uniforms(uint64_t seed, float step, const float* step_dev, float* t_rand_dev, int64_t n_t,
+                      float* u_dev, int64_t n_u, float* sp_points_dev, int64_t n_sp, float sp_radius, void* stream);
 /* model_utils.volumetric_rendering (model_utils.py:176-222).  rgbs [n_rays,n_samples,4] = (rgb, sigma)
  * after activations; outputs comp_rgb [n_rays,3], disp, acc [n_rays], weights [n_rays,n_samples]
  * (disp / acc / weights may be NULL). */

@@ -376,6 +376,18 @@ int pob_sample_coarse(const float* z_base_dev, const float* t_rand_dev, int n_ra
   return 0;
 }
 
+int pob_draw_uniforms(uint64_t seed, float step, const float* step_dev, float* t_rand_dev, int64_t n_t,
+                      float* u_dev, int64_t n_u, float* sp_points_dev, int64_t n_sp, float sp_radius, void* stream) {
+  if (n_t < 0 || n_u < 0 || n_sp < 0) return fail("pob_draw_uniforms", "negative size");
+  if ((n_t && !t_rand_dev) || (n_u && !u_dev) || (n_sp && !sp_points_dev))
+    return fail("pob_draw_uniforms", "NULL pointer");
+  if (sm_count() <= 0) return fail("pob_draw_uniforms", "no sm_100 CUDA device (there is no CPU fallback)");
+  pob_count_launch();
+  POB_CUDA("pob_draw_uniforms", pob::launch_draw_uniforms(seed, step, step_dev, t_rand_dev, n_t, u_dev, n_u,
+                                                          sp_points_dev, n_sp, sp_radius, (cudaStream_t)stream));
+  return 0;
+}
+
 int pob_composite(const float* rgbs_dev, const float* z_dev, const float* dirs_dev, int n_rays, int n_samples,
                   int white_bkgd, float* out_rgb_dev, float* out_disp_dev, float* out_acc_dev,
                   float* out_weights_dev, void* stream) {

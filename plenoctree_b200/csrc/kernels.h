@@ -99,6 +99,11 @@ cudaError_t launch_composite_bwd(const float4* rgbs, const float* z, const float
                                  float gscale, float4* G, float* sq_err_sum, cudaStream_t st);
 cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const float* u, int u_per_ray, int R,
                               int Nc, int Nf, float* z_out, cudaStream_t st);
+// t_rand [n_t], u [n_u] ~ U[0,1), sp [n_sp] ~ U[-radius, radius): Philox4x32-10 keyed by seed, counter (index, stream, step);
+// step_dev (device float, optional) overrides `step` so that a captured graph draws fresh numbers on every replay
+cudaError_t launch_draw_uniforms(unsigned long long seed, float step, const float* step_dev, float* t_rand,
+                                 long long n_t, float* u, long long n_u, float* sp, long long n_sp, float sp_radius,
+                                 cudaStream_t st);
 // rgbs[i].w = relu(sigma) of the sparsity points (as the OUT_RGBS epilogue leaves it); G[i] = (0,0,0, dL/dsigma_raw)
 cudaError_t launch_sparsity_grad(const float4* rgbs, int n, float length, float coef, float4* G,
                                  float* exp_sum, cudaStream_t st);

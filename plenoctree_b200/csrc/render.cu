@@ -360,6 +360,50 @@ __global__ void sparsity_grad_kernel(const float4* __restrict__ rgbs, int n, flo
   if ((threadIdx.x & 31) == 0 && exp_sum) atomicAdd(exp_sum, e);
 }
 
+// ---- random draws of one training step (stratified jitter, inverse-CDF uniforms, sparsity points) ----------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = (element / 4, stream id, step), key = seed: one launch replaces
+// the seven ATen launches (3 x rand + scale / shift) of a step.  The reference draws from jax.random's threefry
+// streams, which cannot be reproduced without JAX; parity tests inject their draws instead (SURVEY.md 7.2 RNG).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// 24 random bits -> [0, 1): never 1, like random.uniform
+__device__ __forceinline__ float u01(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }
+
+__global__ void draw_uniforms_kernel(unsigned long long seed, float step_host, const float* __restrict__ step_dev,
+                                     float* __restrict__ t_rand, long long n_t, float* __restrict__ u, long long n_u,
+                                     float* __restrict__ sp, long long n_sp, float sp_radius) {
+  const uint32_t step = uint32_t(step_dev ? __ldg(step_dev) : step_host);
+  const long long q4 = (n_t + 3) / 4, r4 = (n_u + 3) / 4, s4 = (n_sp + 3) / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q4 + r4 + s4;
+       i += (long long)gridDim.x * blockDim.x) {
+    int stream = 0;
+    long long j = i;
+    float* dst = t_rand;
+    long long n = n_t;
+    if (j >= q4) { j -= q4; stream = 1; dst = u; n = n_u; }
+    if (stream == 1 && j >= r4) { j -= r4; stream = 2; dst = sp; n = n_sp; }
+    const uint4 r = philox4x32_10(make_uint4(uint32_t(j), uint32_t(j >> 32), uint32_t(stream), step),
+                                  make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+    float v[4] = {u01(r.x), u01(r.y), u01(r.z), u01(r.w)};
+    if (stream == 2) {   // random.uniform(key, (npoints, 3), minval=-radius, maxval=radius)  (train.py:79)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 2.0f * sp_radius, -sp_radius);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * j + k < n) dst[4 * j + k] = v[k];
+  }
+}
+
 template <typename F>
 cudaError_t dispatch_seg(int N, F&& f) {
   const int S = (N + 31) / 32;
@@ -417,6 +461,16 @@ cudaError_t launch_sample_pdf(const float* z_c, const float* weights, const floa
   PdfArgs a{z_c, weights, u, u_per_ray, R, Nc, Nf, z_out};
   const unsigned grid = (R + RAYS_PER_BLOCK - 1) / RAYS_PER_BLOCK;
   sample_pdf_kernel<<<grid, RAYS_PER_BLOCK * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_draw_uniforms(unsigned long long seed, float step, const float* step_dev, float* t_rand,
+                                 long long n_t, float* u, long long n_u, float* sp, long long n_sp, float sp_radius,
+                                 cudaStream_t st) {
+  const long long work = (n_t + 3) / 4 + (n_u + 3) / 4 + (n_sp + 3) / 4;
+  if (work == 0) return cudaSuccess;
+  const int grid = int((work + 255) / 256 < 2048 ? (work + 255) / 256 : 2048);
+  draw_uniforms_kernel<<<grid, 256, 0, st>>>(seed, step, step_dev, t_rand, n_t, u, n_u, sp, n_sp, sp_radius);
   return cudaGetLastError();
 }
 

@@ -47,6 +47,7 @@ class TrainState:
         self.gbuf = torch.zeros(model.params.numel() + 8, dtype=torch.float32, device=model.device)
         # device copy of (lr, step) for replayable graphs, bucket-overlap plumbing (created on first use)
         self.lr_step = torch.zeros(2, dtype=torch.float32, device=model.device)
+        self.rng_seed = 20200823 + 7919 * (dist.get_rank() if dist.is_available() and dist.is_initialized() else 0)
         self.side_stream = None
         self.ev_mlp0 = None
         self.ev_bucket0 = None
@@ -67,7 +68,7 @@ def default_loss_scale(n_rays):
 
 def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
                   randomized=True, t_rand=None, u=None, sp_points=None, loss_scale=None, z_fine=None,
-                  sigma_noise=None, mlp0_event=None):
+                  sigma_noise=None, mlp0_event=None, lr_step_on_device=False):
     """value_and_grad(loss_fn) for this rank's shard; fills state.grads / state.stats_raw (device).
     mlp0_event (torch.cuda.Event): recorded on the current stream once the MLP_0 half of the gradient is final."""
     rays = batch["rays"]
@@ -76,8 +77,11 @@ def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.0
     v = _cuda_f32(rays.viewdirs, "rays.viewdirs", 3)
     px = _cuda_f32(batch["pixels"], "pixels")[..., :3].contiguous()
     n = o.shape[0]
-    t_rand, u, upr = model._uniforms(n, randomized, t_rand, u)
     use_sp = sparsity_weight > 0.0 and model.sparsity_npoints > 0
+    if randomized and t_rand is None and (u is None or model.num_fine_samples == 0) and (sp_points is None or not use_sp):
+        # all of the step's draws in one launch of the library's Philox kernel (state.rng_seed, state.step)
+        t_rand, u, sp_points = _draw(model, state, n, use_sp, sparsity_radius, lr_step_on_device)
+    t_rand, u, upr = model._uniforms(n, randomized, t_rand, u)
     if use_sp:
         if sp_points is None:
             # random.uniform(key, (npoints,3), minval=-radius, maxval=radius)  (train.py:79)
@@ -97,6 +101,26 @@ def loss_and_grad(model, state, batch, sparsity_weight=1e-3, sparsity_length=0.0
                                 ptr(state.stats_raw), ptr(ws),
                                 mlp0_event.cuda_event if mlp0_event is not None else None, stream_ptr()))
     return n
+
+
+def _draw(model, state, n, use_sp, sparsity_radius, step_on_device):
+    """t_rand [n,Nc], u [n,Nf] ~ U[0,1) and sp_points [npoints,3] ~ U[-radius,radius) of this step, written by
+    lib.pob_draw_uniforms into buffers the state owns (replaces random.uniform at model_utils.py:137,262 and
+    train.py:79).  The counter is the step number: host value, or state.lr_step[1] when the step is graph-replayed."""
+    nc, nf = model.num_coarse_samples, model.num_fine_samples
+    nsp = model.sparsity_npoints if use_sp else 0
+    key = (n, nsp)
+    if getattr(state, "_draw_key", None) != key:
+        state._draw_buf = torch.empty(n * nc + n * nf + 3 * nsp, dtype=torch.float32, device=model.device)
+        state._draw_key = key
+    buf = state._draw_buf
+    t_rand = buf[:n * nc].view(n, nc)
+    u = buf[n * nc:n * (nc + nf)].view(n, nf) if nf > 0 else None
+    sp = buf[n * (nc + nf):].view(nsp, 3) if nsp > 0 else None
+    check(lib.pob_draw_uniforms(int(state.rng_seed), float(state.step),
+                                ptr(state.lr_step[1:]) if step_on_device else None, ptr(t_rand), n * nc,
+                                ptr(u), n * nf, ptr(sp), 3 * nsp, float(sparsity_radius), stream_ptr()))
+    return t_rand, u, sp
 
 
 def stats_from_raw(raw, n_rays, sparsity_weight, sparsity_npoints, two_level, world=1):
@@ -162,7 +186,7 @@ def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.
         # recorded inside pob_loss_and_grad), hidden under the MLP_1 backward; [MLP_1 | stats] follows on this stream
         side, ev_mlp0, ev_b0 = _bucket_plumbing(state)
         n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand,
-                          u, sp_points, loss_scale, mlp0_event=ev_mlp0)
+                          u, sp_points, loss_scale, mlp0_event=ev_mlp0, lr_step_on_device=lr_step_on_device)
         side.wait_event(ev_mlp0)
         with torch.cuda.stream(side):
             dist.all_reduce(state.gbuf[:P], op=dist.ReduceOp.SUM)
@@ -171,7 +195,7 @@ def train_step(model, state, batch, lr, sparsity_weight=1e-3, sparsity_length=0.
         torch.cuda.current_stream().wait_event(ev_b0)
     else:
         n = loss_and_grad(model, state, batch, sparsity_weight, sparsity_length, sparsity_radius, randomized, t_rand,
-                          u, sp_points, loss_scale)
+                          u, sp_points, loss_scale, lr_step_on_device=lr_step_on_device)
         if world > 1:
             allreduce_gradients(state.gbuf)   # pmean(grad) and pmean(stats) in one bucket
     # weight_l2 = sum(theta^2)/numel  ->  d/dtheta = 2*theta/numel  (train.py:101-108,114)

@@ -284,3 +284,29 @@ def test_training_curve_matches_oracle():
     cos = float(np.dot(dp_gpu, dp_ref) / (np.linalg.norm(dp_gpu) * np.linalg.norm(dp_ref)))
     _record("training_curve_6_steps", dict(curve=curve, update_rel_l2=rel, update_cosine=cos))
     assert rel < 0.15 and cos > 0.99, (rel, cos)
+
+
+@pytest.mark.gpu
+def test_draw_uniforms_philox():
+    """pob_draw_uniforms: U[0,1) jitter / inverse-CDF draws and U[-r,r) sparsity points of a step from one Philox
+    launch: ranges, moments, determinism in (seed, step), fresh numbers per step, device-side step override."""
+    from plenoctree_b200._lib import check, lib, ptr
+    n_t, n_u, n_sp = 4096 * 64 + 3, 4096 * 128 + 1, 3 * 10000
+    def draw(seed, step, step_dev=None):
+        t = torch.empty(n_t, device="cuda"); u = torch.empty(n_u, device="cuda"); sp = torch.empty(n_sp, device="cuda")
+        check(lib.pob_draw_uniforms(seed, float(step), ptr(step_dev), ptr(t), n_t, ptr(u), n_u, ptr(sp), n_sp, 1.5, None))
+        torch.cuda.synchronize()
+        return t, u, sp
+    t, u, sp = draw(7, 3)
+    for x in (t, u):
+        assert float(x.min()) >= 0.0 and float(x.max()) < 1.0
+        assert abs(float(x.mean()) - 0.5) < 2e-3 and abs(float(x.var()) - 1.0 / 12.0) < 2e-3
+    assert float(sp.min()) >= -1.5 and float(sp.max()) < 1.5 and abs(float(sp.mean())) < 0.03
+    assert abs(float(torch.corrcoef(torch.stack([t[:100000], u[:100000]]))[0, 1])) < 0.02     # streams are independent
+    t2, u2, sp2 = draw(7, 3)
+    assert torch.equal(t, t2) and torch.equal(u, u2) and torch.equal(sp, sp2)
+    t3, _, _ = draw(7, 4)
+    t4, _, _ = draw(8, 3)
+    assert not torch.equal(t, t3) and not torch.equal(t, t4)
+    t5, _, _ = draw(7, 999, step_dev=torch.tensor([4.0], device="cuda"))      # the device step wins
+    assert torch.equal(t5, t3)
