@@ -124,7 +124,7 @@ def c4_extraction(dev, peak_tflops, depth=8, samples_per_cell=256, keep_fraction
     nerf = NerfModel(sh_deg=3, num_coarse_samples=64, num_fine_samples=128, max_rays=4096, device=dev)
     nerf.init_params(20200823)
     radius, center = [1.5] * 3, [0.0] * 3
-    tree = N3Tree(N=2, data_dim=49, init_refine=0, init_reserve=500000, geom_resize_fact=1.0, depth_limit=depth,
+    tree = N3Tree(N=2, data_dim=49, init_refine=0, init_reserve=2200000, geom_resize_fact=1.0, depth_limit=depth,
                   radius=radius, center=center, data_format="SH16", map_location=dev)
     offset, scale = tree.offset.tolist(), tree.invradius.tolist()
     x0, nx = ops.grid_slab(reso, rank, world)
@@ -144,6 +144,7 @@ def c4_extraction(dev, peak_tflops, depth=8, samples_per_cell=256, keep_fraction
         hold["raw"] = None
         hold["raw"] = ops.eval_grid(nerf._blob(False), 3, reso, offset, scale, x0=x0, nx=nx, want_rgb=True,
                                     precision=nerf.precision, device=dev)
+    sweep_raw(0)                      # first call pays the cudaMalloc of the 26 GB / world output
     ms = timed_ms(sweep_raw, dev, reps=1)
     hold["raw"] = None
     res["sigma_sh_sweep_ms"] = ms
