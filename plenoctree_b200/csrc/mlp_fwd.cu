@@ -701,7 +701,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
 }
 
 template <int OUTM, bool SAVE>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 mlp_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   fwd_body<1, OUTM, SAVE, true>(p, smem);
