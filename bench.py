@@ -19,7 +19,7 @@ sparsity points per step (the reference draws those per device, nerf_sh/train.py
 `roofline`: dominant kernel class (and, under `kernels`, all three), algorithmic GEMM FLOPs (SURVEY.md §8d:
            1,007,104 fwd / 942,592 dgrad / 1,007,104 wgrad FLOP per MLP-sample, SH16) / CUDA-event kernel time,
            vs the measured sustained bf16 tensor peak in MEASURED_PEAKS.json; `step_frac` = the whole step.
-`strong`, `tt_sh25`, `c4_extraction`, `c5_octree_opt`: the other BASELINE configurations, timed after the main
+`strong`, `tt_sh25`, `c4_extraction`, `c5_octree_opt`, `render_eval`: the other BASELINE configurations, timed after the main
            region on the same ranks (bench_extras.py); skipped with --no-extras.
 """
 import argparse
@@ -363,7 +363,8 @@ def main():
         for key, fn in (("strong", lambda: X.strong_scaling(dev, peaks["tflops"], steps=max(K, 20))),
                         ("tt_sh25", lambda: X.strong_scaling(dev, peaks["tflops"], steps=max(K, 20), tt=True)),
                         ("c4_extraction", lambda: X.c4_extraction(dev, peaks["tflops"])),
-                        ("c5_octree_opt", lambda: X.c5_octree_opt(dev))):
+                        ("c5_octree_opt", lambda: X.c5_octree_opt(dev)),
+                        ("render_eval", lambda: X.render_eval(dev))):
             try:
                 torch.cuda.empty_cache()
                 extras[key] = fn()

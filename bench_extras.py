@@ -13,6 +13,8 @@ so the other configurations BASELINE names are timed here, after the main region
                  tree build and step 2 at samples_per_cell 256 (octree/extraction.py:288-394), timed per stage.
   c5_octree_opt  configs[4]: octree.optimization on a 256^3-equivalent SH16 tree, ray-parallel (row slabs per rank,
                  gradient exchange per image, replicated SGD: the reference's sequential per-image updates).
+  render_eval    nerf_sh.eval's render loop: 800x800 test-mode frames through utils.render_image, chunks split over
+                 the ranks.
 
 Every timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 """
@@ -99,6 +101,30 @@ def strong_scaling(dev, peak_tflops, steps=30, tt=False, global_batch=4096, nsp=
         out["ms_per_step_one_gpu_same_batch"] = ms_1
         out["efficiency_vs_n1"] = ms_1 / (world * ms_n)
     return out
+
+
+def render_eval(dev, frames=2, hw=800):
+    """a14 / nerf_sh.eval: full test-mode frames (randomized False, 64 + 128 samples) through utils.render_image;
+    every chunk is split over the ranks and all-gathered (nerf_sh/nerf/utils.py:331-381, 701-706)."""
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf.utils import generate_rays, pose_spherical, render_image
+    world = _world()
+    model = NerfModel(sh_deg=3, num_coarse_samples=64, num_fine_samples=128, max_rays=8192, device=dev)
+    model.init_params(20200823)
+    focal = 0.5 * hw / math.tan(0.5 * 0.6911112070083618)
+    rs = np.random.RandomState(20200823)
+    poses = np.stack([pose_spherical(rs.uniform(-180, 180), rs.uniform(-90, 0), 4.0) for _ in range(frames)])
+    rays = generate_rays(hw, hw, focal, poses)
+    frames_dev = [Rays(*[torch.from_numpy(np.ascontiguousarray(r[i])).to(dev) for r in rays]) for i in range(frames)]
+    chunk = 8192 * world
+
+    def one(i):
+        render_image(model, frames_dev[i % frames], chunk=chunk)
+    one(0)
+    ms = timed_ms(one, dev, reps=frames)
+    flop = hw * hw * 256 * F_SH16[0]
+    return {"n_gpus": world, "image": f"{hw}x{hw}", "ms_per_frame": ms, "value": hw * hw / ms * 1e3, "unit": "rays/s",
+            "chunk_rays": chunk, "tflops_algorithmic": flop / (ms * 1e-3) / 1e12}
 
 
 class _SynthCams:

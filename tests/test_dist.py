@@ -163,3 +163,46 @@ def test_extraction_two_ranks_equals_one_rank():
         assert np.array_equal(child, child1), rank
         # identical sample positions; the per-cell mean is accumulated with float atomics (order-dependent rounding)
         assert np.abs(data - data1).max() <= 1e-5 * np.abs(data1).max(), rank
+
+
+def _render_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # both ranks share cuda:0 (see _octree_worker)
+    try:
+        import numpy as np
+        from plenoctree_b200.nerf.models import NerfModel, Rays
+        from plenoctree_b200.nerf.utils import generate_rays, pose_spherical, render_image
+        torch.cuda.set_device(0)
+        model = NerfModel(sh_deg=3, max_rays=512)
+        model.init_params(7)
+        rays = generate_rays(37, 29, 40.0, np.stack([pose_spherical(30.0, -40.0, 4.0)]))
+        rgb, disp, acc = render_image(model, Rays(rays.origins[0], rays.directions[0], rays.viewdirs[0]), chunk=700)
+        q.put((rank, rgb.cpu().numpy(), disp.cpu().numpy(), acc.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_render_image_two_ranks_equals_one_rank():
+    """a14 (nerf_sh/nerf/utils.py:331-381, 701-706): every chunk of an image is split over the ranks and all-gathered;
+    rays are independent, so two ranks must return exactly the single-process image (ragged last chunk included)."""
+    import numpy as np
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf.utils import generate_rays, pose_spherical, render_image
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 977) % 2000
+    procs = [ctx.Process(target=_render_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    model = NerfModel(sh_deg=3, max_rays=512)
+    model.init_params(7)
+    rays = generate_rays(37, 29, 40.0, np.stack([pose_spherical(30.0, -40.0, 4.0)]))
+    rgb, disp, acc = render_image(model, Rays(rays.origins[0], rays.directions[0], rays.viewdirs[0]), chunk=700)
+    for _, r_rgb, r_disp, r_acc in res:
+        assert np.array_equal(r_rgb, rgb.cpu().numpy())
+        assert np.array_equal(r_disp, disp.cpu().numpy()) and np.array_equal(r_acc, acc.cpu().numpy())
