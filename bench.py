@@ -313,6 +313,19 @@ def main():
     launches0 = _lib.lib.pob_launch_count()
     ms_total = timed(step_resident, W)
     launches = int(_lib.lib.pob_launch_count() - launches0)
+    # ---- per-step distribution over a longer run (the contract region above is K steps long; the driver's K = 20
+    # is 80 ms): every step bracketed by its own pair of events, no host sync inside the loop
+    ND = 100
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(ND + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(ND):
+        step_resident(W + K + i)
+        evs[i + 1].record()
+    barrier()
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(ND))
+    step_dist = {"steps": ND, "min_ms": per[0], "median_ms": per[ND // 2], "p90_ms": per[int(ND * 0.9)], "max_ms": per[-1],
+                 "mean_ms": sum(per) / ND}
     # ---- end-to-end (host buffers) ----
     for i in range(W):
         step_e2e(K + W + i)
@@ -393,6 +406,7 @@ def main():
                     "h2d_bytes_per_step": RAYS * 12 * 4, "d2h_bytes_per_step": 8 * 4},
             "gpu_launches": launches,
             "kernel_ms_per_step": per_step_ms,
+            "step_ms_distribution": step_dist,
             "step_tflops_algorithmic": FLOP_PER_STEP * f_scale / (ms_total / K * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,

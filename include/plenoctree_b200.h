@@ -191,7 +191,7 @@ int pob_adam_update(int sh_deg, int num_mlps, float* params_dev, const float* gr
                     float weight_decay_coef, void* packed_coarse_dev, void* packed_fine_dev, void* stream);
 
 /* Profiling aid: pob_eval_points_raw (sigma only, FP16) that also records clock64() stamps of CTA 0 into
- * trace_dev[3][256] (role 0 = MMA issuer, 1/2 = first epilogue warp of tile X/Y); scripts/trace_fwd.py.
+ * trace_dev[3][256] (role 0 = MMA issuer, 1/2 = first epilogue warp of tile X/Y); scripts/trace_summary.py.
  * save_*_dev (all or none; sized like the training workspace: 512 KB, 16 KB and 4 KB per 128 samples) turn
  * on the training-mode stores so their cost shows in the trace. */
 int pob_debug_trace_fwd(const void* packed_dev, int sh_deg, const float* points_dev, int64_t m,

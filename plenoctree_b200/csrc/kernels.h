@@ -133,8 +133,8 @@ struct WgradSegment {
   const uint8_t *h, *dz, *e, *d_o;
 };
 struct WgradParams {
-  WgradSegment seg[2];
-  long long seg_tiles[2];
+  WgradSegment seg;         // one level's tile arrays (its sparsity points ride behind the ray samples)
+  long long seg_tiles;
   int NH;
   float* partials;          // [num_ctas][WG_PARTIAL_FLOATS]
   short cta_role[WG_MAX_CTAS], cta_index[WG_MAX_CTAS], cta_count[WG_MAX_CTAS];
@@ -148,7 +148,7 @@ cudaError_t launch_mlp_wgrad(const WgradParams& p, int num_ctas, cudaStream_t st
 // partials of one wgrad launch -> flat gradient of one MLP (reference layout), times inv_scale
 cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_NUM_ROLES],
                                 const int role_count[WG_NUM_ROLES], int K, float inv_scale,
-                                float* grad_flat, cudaStream_t stream, const float* partials2 = nullptr);
+                                float* grad_flat, cudaStream_t stream);
 // flax.optim.Adam.apply_gradient on a flat buffer; grad is multiplied by grad_mult first
 // lr_step_dev (optional, device [2] = {lr, step}) overrides the host lr / step: a captured graph replays with new values
 cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, long long n, float lr,

@@ -41,7 +41,6 @@ namespace {
 
 struct ReduceArgs {
   const float* partials;
-  const float* partials2;   // optional second launch with the same role tables (sparsity level)
   int role_start[WG_NUM_ROLES], role_count[WG_NUM_ROLES];
   FlatLayout L;
   int K, NH;
@@ -94,10 +93,6 @@ __device__ __forceinline__ float sum_partials(const ReduceArgs& a, int role, int
   float s = 0.f;
   const float* p = a.partials + size_t(a.role_start[role]) * WG_PARTIAL_FLOATS + off;
   for (int c = 0; c < a.role_count[role]; ++c) s += p[size_t(c) * WG_PARTIAL_FLOATS];
-  if (a.partials2) {
-    const float* p2 = a.partials2 + size_t(a.role_start[role]) * WG_PARTIAL_FLOATS + off;
-    for (int c = 0; c < a.role_count[role]; ++c) s += p2[size_t(c) * WG_PARTIAL_FLOATS];
-  }
   return s;
 }
 
@@ -166,10 +161,9 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 
 cudaError_t launch_reduce_grads(const float* partials, const int role_start[WG_NUM_ROLES],
                                 const int role_count[WG_NUM_ROLES], int K, float inv_scale,
-                                float* grad_flat, cudaStream_t stream, const float* partials2) {
+                                float* grad_flat, cudaStream_t stream) {
   ReduceArgs a;
   a.partials = partials;
-  a.partials2 = partials2;
   for (int r = 0; r < WG_NUM_ROLES; ++r) {
     a.role_start[r] = role_start[r];
     a.role_count[r] = role_count[r];

@@ -286,8 +286,8 @@ int pob_loss_and_grad(const pob_render_config* cfg, const pob_train_hparams* hp,
     { pob_count_launch(); PobPhaseTimer _t(POB_PH_BWD, st); POB_CUDA(where, launch_mlp_bwd(b, sms, st)); }
     WgradParams g;
     memset(&g, 0, sizeof(g));
-    g.seg[0] = WgradSegment{L.H, L.DZ, L.E, L.DO};
-    g.seg_tiles[0] = tiles_for(Mm);
+    g.seg = WgradSegment{L.H, L.DZ, L.E, L.DO};
+    g.seg_tiles = tiles_for(Mm);
     g.NH = NH;
     g.partials = w.partials[mlp];
     int rs[WG_NUM_ROLES], rc[WG_NUM_ROLES];

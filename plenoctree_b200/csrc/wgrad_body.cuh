@@ -92,16 +92,14 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p, uint8_t* smem, 
   const RoleInfo R = role_info(role < 0 ? 0 : role, p.NH);
   const uint32_t b_half_bytes = uint32_t(R.b_chunks) * WG_SUB * 128;
 
-  // work list: tiles t = ridx + i*rcnt over the (at most two) segments
-  const long long total_tiles = p.seg_tiles[0] + p.seg_tiles[1];
+  // work list: tiles t = ridx + i*rcnt
+  const long long total_tiles = p.seg_tiles;
   const long long n_items = role < 0 ? 0 : ((total_tiles > ridx) ? (total_tiles - ridx + rcnt - 1) / rcnt : 0);
 
   auto get_item = [&](long long i) -> WgItem {
     WgItem it;
-    const long long t = ridx + i * rcnt;
-    const int seg = t < p.seg_tiles[0] ? 0 : 1;
-    const long long lt = seg ? t - p.seg_tiles[0] : t;
-    const WgradSegment& sg = p.seg[seg];
+    const long long lt = ridx + i * rcnt;
+    const WgradSegment& sg = p.seg;
     it.a_ptr = (R.a_kind == 0 ? sg.dz : sg.h) + (size_t(lt) * NUM_TRUNK + R.a_layer) * A_TILE_BYTES;
     if (R.b_kind == 0) it.b_ptr = sg.h + (size_t(lt) * NUM_TRUNK + R.b_layer) * A_TILE_BYTES;
     else if (R.b_kind == 1) it.b_ptr = sg.e + size_t(lt) * E_TILE_BYTES;

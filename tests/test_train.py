@@ -310,3 +310,35 @@ def test_draw_uniforms_philox():
     assert not torch.equal(t, t3) and not torch.equal(t, t4)
     t5, _, _ = draw(7, 999, step_dev=torch.tensor([4.0], device="cuda"))      # the device step wins
     assert torch.equal(t5, t3)
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (one CUDA graph per step: Philox draws keyed by the device-side step, kernels, Adam with
+    lr / step from the device buffer) must reproduce the eager train_step sequence bit for bit."""
+    from plenoctree_b200.nerf.models import NerfModel, Rays
+    from plenoctree_b200.nerf import train as T
+    R = 256
+    fc, ff, rays, px, _, _, _ = _setup(3, R, 128, 0, 33)
+    b12 = torch.from_numpy(np.concatenate([rays[0], rays[1], rays[2], px], axis=1)).cuda()
+    lrs = [5e-4, 4e-4, 3e-4, 2e-4]
+    outs = []
+    for graphed in (False, True):
+        model = NerfModel(sh_deg=3, max_rays=R, sparsity_npoints=1000)
+        model.set_params(np.concatenate([fc, ff]))
+        state = T.TrainState(model)
+        if graphed:
+            g = T.GraphedTrainStep(model, state, R)
+            assert state.step == 0
+            for lr in lrs:
+                g.step(b12, lr)
+        else:
+            batch = {"rays": Rays(b12[:, 0:3], b12[:, 3:6], b12[:, 6:9]), "pixels": b12[:, 9:12]}
+            for lr in lrs:
+                T.train_step(model, state, batch, lr)
+        torch.cuda.synchronize()
+        assert state.step == len(lrs)
+        outs.append((model.params.clone(), state.m.clone(), state.v.clone(), state.stats_raw.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[0][0], torch.from_numpy(np.concatenate([fc, ff])).cuda())
