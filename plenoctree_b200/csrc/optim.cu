@@ -135,18 +135,22 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a) {
   }
 }
 
+// lr / step come from the launch arguments or, when lr_step is given, from device memory (replayable CUDA graphs);
+// the bias corrections 1 - beta^t are formed in the kernel either way (-expm1f(t log beta): accurate for small t
+// where 1 - powf(beta, t) cancels), so that an eager step and a graph-replayed one are bit-identical
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float bc1, float bc2,
+                            float* __restrict__ v, long long n, float lr, float step,
                             const float* __restrict__ lr_step, float beta1, float beta2, float eps, float grad_mult,
                             float wd) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (lr_step) {   // learning rate and step count live on the device (replayable CUDA graphs)
+  if (lr_step) {
     lr = __ldg(lr_step);
-    const float t = __ldg(lr_step + 1) + 1.0f;
-    bc1 = 1.0f - powf(beta1, t);
-    bc2 = 1.0f - powf(beta2, t);
+    step = __ldg(lr_step + 1);
   }
+  const float t = step + 1.0f;
+  const float bc1 = -expm1f(t * logf(beta1));
+  const float bc2 = -expm1f(t * logf(beta2));
   const float p = param[i];
   const float g = grad[i] * grad_mult + wd * p;
   const float mi = (1.0f - beta1) * g + beta1 * m[i];
@@ -181,11 +185,8 @@ cudaError_t launch_adam(float* param, const float* grad, float* m, float* v, lon
                         float step, const float* lr_step_dev, float beta1, float beta2, float eps, float grad_mult,
                         float weight_decay_coef, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const double t = double(step) + 1.0;
-  const float bc1 = float(1.0 - pow(double(beta1), t));
-  const float bc2 = float(1.0 - pow(double(beta2), t));
-  adam_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, bc1, bc2, lr_step_dev,
-                                                              beta1, beta2, eps, grad_mult, weight_decay_coef);
+  adam_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(param, grad, m, v, n, lr, step, lr_step_dev, beta1,
+                                                              beta2, eps, grad_mult, weight_decay_coef);
   return cudaGetLastError();
 }
 

@@ -103,6 +103,14 @@ class Module:
     def variable(self, col, name, init, *args):
         return types.SimpleNamespace(value=init(*args))
 
+    def apply(self, variables, *args, method=None, **kw):
+        """model.apply(variables, ...): bind {"params": {"MLP_i": {"Dense_j": {"kernel", "bias"}}}} to the
+        sub-modules (flax's own tree layout, octree/nerf/models.py:75-87), then call `method` or __call__."""
+        for name, layers in variables["params"].items():
+            sub = getattr(self, name)
+            sub._params = [(layers[f"Dense_{j}"]["kernel"], layers[f"Dense_{j}"]["bias"]) for j in range(len(layers))]
+        return (method or self.__call__)(*args, **kw)
+
 
 def compact(fn):
     """@nn.compact: while the method runs, nn.Dense layers take their (kernel, bias) in creation order —
@@ -138,6 +146,18 @@ def _make_linen():
     return nn
 
 
+def _tree_leaves(t):
+    if isinstance(t, dict):
+        for k in sorted(t):
+            yield from _tree_leaves(t[k])
+    else:
+        yield t
+
+
+def _tree_map(fn, t):
+    return {k: _tree_map(fn, v) for k, v in t.items()} if isinstance(t, dict) else fn(t)
+
+
 def install():
     """register the stand-ins in sys.modules; returns the names so that the caller can remove them again."""
     jax = types.ModuleType("jax")
@@ -148,14 +168,54 @@ def install():
     jnn = types.ModuleType("jax.nn")
     jnn.initializers = types.SimpleNamespace(glorot_uniform=lambda: None)
     jnn.relu = lambda x: np.maximum(x, np.float32(0)).astype(np.float32)
+    lax.pmean = lambda x, axis_name=None: x                      # one device
     jax.numpy, jax.random, jax.lax, jax.nn = jnp, random, lax, jnn
+    # jax.value_and_grad: the VALUE side runs the reference's loss_fn; gradients cannot be taken of numpy code and
+    # are returned as zeros (the oracle's gradient is autograd of its pinned forward)
+    def value_and_grad(fn, has_aux=False):
+        def g(x):
+            return fn(x), _tree_map(lambda a: np.zeros_like(a), x)
+        return g
+    jax.value_and_grad = value_and_grad
+    tree_util = types.ModuleType("jax.tree_util")
+    def tree_reduce(f, tree, initializer=None):
+        acc = initializer
+        for leaf in _tree_leaves(tree):
+            acc = f(acc, leaf)
+        return acc
+    tree_util.tree_reduce = tree_reduce
+    jax.tree_util = tree_util
+    jax.config = types.SimpleNamespace(parse_flags_with_absl=lambda: None)
+    cfg_mod = types.ModuleType("jax.config")
+    jax.dlpack = types.ModuleType("jax.dlpack")
+    jax.scipy = types.ModuleType("jax.scipy")
+    jax.host_id = lambda: 0
+    jax.host_count = lambda: 1
+    jax.local_device_count = lambda: 1
+    jax.device_count = lambda: 1
     flax = types.ModuleType("flax")
     linen = _make_linen()
     flax.linen = linen
-    mods = {"jax": jax, "jax.numpy": jnp, "jax.random": random, "jax.lax": lax, "jax.nn": jnn, "flax": flax,
-            "flax.linen": linen}
+    import dataclasses
+    flax.struct = types.SimpleNamespace(dataclass=lambda cls: _with_replace(dataclasses.dataclass(cls)))
+    flax.optim = types.SimpleNamespace(Optimizer=object)
+    metrics = types.ModuleType("flax.metrics")
+    metrics.tensorboard = types.ModuleType("flax.metrics.tensorboard")
+    training = types.ModuleType("flax.training")
+    training.checkpoints = types.ModuleType("flax.training.checkpoints")
+    flax.metrics, flax.training = metrics, training
+    mods = {"jax": jax, "jax.numpy": jnp, "jax.random": random, "jax.lax": lax, "jax.nn": jnn, "jax.tree_util": tree_util,
+            "jax.dlpack": jax.dlpack, "jax.scipy": jax.scipy, "flax": flax, "flax.linen": linen, "flax.metrics": metrics,
+            "flax.metrics.tensorboard": metrics.tensorboard, "flax.training": training,
+            "flax.training.checkpoints": training.checkpoints}
     sys.modules.update(mods)
     return list(mods)
+
+
+def _with_replace(cls):
+    import dataclasses
+    cls.replace = lambda self, **kw: dataclasses.replace(self, **kw)
+    return cls
 
 
 def uninstall(names):

@@ -268,6 +268,91 @@ def gen_ref_render():
     print("ref_render.npz", len(out), "arrays")
 
 
+def gen_ref_loss():
+    """Execute the reference's train_step (nerf_sh/train.py:51-121) up to its loss value: loss_fn — the two MSE
+    terms, the sparsity term on injected points, weight_l2, the PSNRs — runs unmodified over the numpy stand-ins
+    (jax.value_and_grad returns loss_fn's value and zero gradients; pmean and apply_gradient are identities)."""
+    import collections
+    import dataclasses
+    import types
+    import jax_stub
+    names = jax_stub.install()
+    fake_ds = types.ModuleType("nerf_sh.nerf.datasets")       # loaders: not on this path (define_flags lists the names)
+    fake_ds.dataset_dict = {"blender": None, "llff": None, "nsvf": None}
+    sys.modules["nerf_sh.nerf.datasets"] = fake_ds
+    try:
+        from absl import flags
+        import nerf_sh.train as RT            # defines the reference's flags (utils.define_flags) at import
+        from nerf_sh.nerf import models as RM, utils as RU
+        import flax.linen as nn
+        FLAGS = flags.FLAGS
+        FLAGS(["make_golden"])
+        sh_deg, B, N, NF, NSP = 3, 16, 64, 128, 40
+        FLAGS.randomized = True
+        FLAGS.sparsity_weight = 1e-3
+        FLAGS.sparsity_npoints = NSP
+        FLAGS.sparsity_radius = 1.5
+        FLAGS.sparsity_length = 0.05
+        FLAGS.weight_decay_mult = 0.25
+        rs = np.random.RandomState(777)
+        poses = np.stack([O.pose_spherical(rs.uniform(-180, 180), rs.uniform(-90, 0), 4.0) for _ in range(3)])
+        rays_all = O.generate_rays(40, 30, 55.5, poses)
+        pick = rs.choice(3 * 30 * 40, B, replace=False)
+        o, d, v = [np.ascontiguousarray(np.asarray(r).reshape(-1, 3)[pick]).astype(np.float32) for r in rays_all]
+        px = rs.uniform(size=(B, 3)).astype(np.float32)
+        t_rand = rs.uniform(size=(B, N)).astype(np.float32)
+        u_f = rs.uniform(size=(B, NF)).astype(np.float32)
+        sp01 = rs.uniform(size=(NSP, 3)).astype(np.float32)
+        flat_c = O.init_flat_params(sh_deg, 6101, bias_scale=0.05)
+        flat_f = O.init_flat_params(sh_deg, 6102, bias_scale=0.05)
+
+        def ptree(flat):
+            return {f"Dense_{j}": {"kernel": w.numpy(), "bias": b.numpy()} for j, (w, b) in enumerate(O.unflatten(flat, sh_deg))}
+        variables = {"params": {"MLP_0": ptree(flat_c), "MLP_1": ptree(flat_f)}}
+        model = RM.NerfModel(num_coarse_samples=N, num_fine_samples=NF, use_viewdirs=False, sh_deg=sh_deg, sg_dim=-1,
+                             near=2.0, far=6.0, noise_std=None, net_depth=8, net_width=256, net_depth_condition=1,
+                             net_width_condition=128, net_activation=nn.relu, skip_layer=4, num_rgb_channels=48,
+                             num_sigma_channels=1, white_bkgd=True, min_deg_point=0, max_deg_point=10, deg_view=4,
+                             lindisp=False, rgb_activation=nn.sigmoid, sigma_activation=nn.relu,
+                             legacy_posenc_order=False)
+
+        @dataclasses.dataclass
+        class Opt:
+            target: dict
+            def apply_gradient(self, grad, learning_rate=None):
+                return self
+        state = RU.TrainState(optimizer=Opt(variables))
+        # train_step splits rng into (rng, key_0, key_1, key_2): every key carries the injected draws; they are told
+        # apart by shape ([B,N] jitter, [B,NF] inverse-CDF uniforms, [NSP,3] sparsity points)
+        class MultiKey(jax_stub.Key):
+            pass
+        import jax.random as jr
+        table = {tuple(t_rand.shape): t_rand, tuple(u_f.shape): u_f, tuple(sp01.shape): sp01}
+        orig_uniform = jr.uniform
+
+        def uniform(key, shape, dtype=np.float32, minval=0.0, maxval=1.0):
+            base = table[tuple(shape)]
+            return (base * np.float32(maxval - minval) + np.float32(minval)).astype(np.float32)
+        jr.uniform = uniform
+        RT.random.uniform = uniform
+        import nerf_sh.nerf.model_utils as MU
+        MU.random.uniform = uniform
+        batch = {"rays": RU.Rays(o, d, v), "pixels": px}
+        _, stats, _ = RT.train_step(model, jax_stub.Key(seed=1), state, batch, 5e-4)
+        jr.uniform = orig_uniform
+        out = dict(origins=o, directions=d, viewdirs=v, pixels=px, t_rand=t_rand, u=u_f, sp01=sp01, sh_deg=sh_deg,
+                   seeds=np.array([6101, 6102]), sparsity_weight=1e-3, sparsity_radius=1.5, sparsity_length=0.05,
+                   weight_decay_mult=0.25, loss=np.float32(stats.loss), psnr=np.float32(stats.psnr),
+                   loss_c=np.float32(stats.loss_c), psnr_c=np.float32(stats.psnr_c),
+                   loss_sp=np.float32(stats.loss_sp), weight_l2=np.float32(stats.weight_l2))
+    finally:
+        jax_stub.uninstall(names)
+        for k in [k for k in sys.modules if k.startswith("nerf_sh")]:
+            sys.modules.pop(k, None)
+    np.savez_compressed(os.path.join(HERE, "ref_loss.npz"), **out)
+    print("ref_loss.npz", {k: float(out[k]) for k in ("loss", "loss_c", "loss_sp", "weight_l2", "psnr")})
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -308,7 +393,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ref_render":
         gen_ref_render()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_loss":
+        gen_ref_loss()
+        sys.exit(0)
     gen_ref_render()
+    gen_ref_loss()
     gen_eval_points(3, 2048, 20200823, "eval_points_sh16.npz")
     gen_eval_points(4, 512, 20200900, "eval_points_sh25.npz")
     gen_eval_sh()

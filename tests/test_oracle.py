@@ -234,3 +234,25 @@ def test_package_generate_rays_matches_reference(golden_dir):
     np.testing.assert_allclose(rays.origins, g["origins"], rtol=0, atol=0)
     np.testing.assert_allclose(rays.directions, g["directions"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(rays.viewdirs, g["viewdirs"], rtol=1e-6, atol=1e-6)
+
+
+def test_loss_fn_matches_executed_reference_train_step(golden_dir):
+    """train_step.loss_fn (nerf_sh/train.py:68-114) executed unmodified over the numpy stand-ins
+    (tests/golden/make_golden.py::gen_ref_loss): both MSE terms, the PSNRs, the sparsity term on injected points
+    (random.uniform(key, (n,3), minval=-r, maxval=r), train.py:79) and weight_l2 over the whole parameter tree."""
+    g = np.load(os.path.join(golden_dir, "ref_loss.npz"))
+    sh_deg = int(g["sh_deg"])
+    pc = O.unflatten(O.init_flat_params(sh_deg, int(g["seeds"][0]), bias_scale=0.05), sh_deg)
+    pf = O.unflatten(O.init_flat_params(sh_deg, int(g["seeds"][1]), bias_scale=0.05), sh_deg)
+    r = np.float32(g["sparsity_radius"])
+    sp = (g["sp01"] * np.float32(r - (-r)) + np.float32(-r)).astype(np.float32)      # the stand-in's uniform()
+    cfg = dict(num_coarse_samples=64, num_fine_samples=128, near=2.0, far=6.0, white_bkgd=True,
+               sparsity_weight=float(g["sparsity_weight"]), sparsity_length=float(g["sparsity_length"]),
+               weight_decay_mult=float(g["weight_decay_mult"]))
+    with torch.no_grad():
+        total, st = O.loss_fn(pc, pf, sh_deg, (_t(g["origins"]), _t(g["directions"]), _t(g["viewdirs"])),
+                              _t(g["pixels"]), cfg, _t(g["t_rand"]), _t(g["u"]), _t(sp))
+    for k, tol in (("loss", 3e-4), ("loss_c", 2e-5), ("loss_sp", 1e-4), ("weight_l2", 1e-6), ("psnr", 3e-4), ("psnr_c", 2e-5)):
+        assert abs(float(st[k]) - float(g[k])) <= tol * abs(float(g[k])), (k, float(st[k]), float(g[k]))
+    want_total = float(g["loss"]) + float(g["loss_c"]) + float(g["loss_sp"]) + float(g["weight_decay_mult"]) * float(g["weight_l2"])
+    assert abs(float(total) - want_total) < 3e-4 * want_total
