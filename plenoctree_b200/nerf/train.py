@@ -225,12 +225,18 @@ class GraphedTrainStep:
         g.step(batch, lr)            # batch tensors may be host (pinned) or device; copied into the static buffers
     """
 
+    HYPER_SLOTS = 16
+
     def __init__(self, model, state, n_rays, sparsity_weight=1e-3, sparsity_length=0.05, sparsity_radius=1.5,
                  weight_decay_mult=0.0, warmup=3, collective=True):
         self.model, self.state, self.n = model, state, int(n_rays)
         dev = model.device
         self.buf = torch.zeros((self.n, 12), dtype=torch.float32, device=dev)       # [o | d | v | px]
-        self._host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        # (lr, step) staging: a ring of pinned slots, each guarded by an event recorded behind its copy, so that the
+        # host may queue several replays ahead without overwriting a slot whose copy has not executed yet
+        self._host = torch.zeros((self.HYPER_SLOTS, 2), dtype=torch.float32).pin_memory()
+        self._host_done = [None] * self.HYPER_SLOTS
+        self._slot = 0
         self.kw = dict(sparsity_weight=sparsity_weight, sparsity_length=sparsity_length,
                        sparsity_radius=sparsity_radius, weight_decay_mult=weight_decay_mult, lr_step_on_device=True,
                        collective=collective)
@@ -260,9 +266,16 @@ class GraphedTrainStep:
         return {"rays": Rays(b[:, 0:3], b[:, 3:6], b[:, 6:9]), "pixels": b[:, 9:12]}
 
     def _set_hyper(self, lr):
-        self._host[0] = float(lr)
-        self._host[1] = float(self.state.step)
-        self.state.lr_step.copy_(self._host, non_blocking=True)
+        k = self._slot
+        self._slot = (k + 1) % self.HYPER_SLOTS
+        if self._host_done[k] is not None:
+            self._host_done[k].synchronize()
+        self._host[k, 0] = float(lr)
+        self._host[k, 1] = float(self.state.step)
+        self.state.lr_step.copy_(self._host[k], non_blocking=True)
+        ev = self._host_done[k] or torch.cuda.Event()
+        ev.record()
+        self._host_done[k] = ev
 
     def step(self, batch12, lr):
         """batch12: [n_rays, 12] float32 tensor (origins | directions | viewdirs | pixels), host-pinned or device."""
