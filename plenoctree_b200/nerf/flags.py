@@ -127,12 +127,14 @@ def check_scope(args):
         raise NotImplementedError("use_viewdirs (vanilla NeRF colour head) is outside the NeRF-SH path")
     if args.sg_dim > 0:
         raise NotImplementedError("spherical gaussians (sg_dim) are outside the NeRF-SH path")
-    if args.dataset not in ("blender", "nsvf"):
-        raise NotImplementedError(f"dataset {args.dataset!r}: the Blender and NSVF formats are loaded here (LLFF/NDC is not)")
+    if args.dataset not in ("blender", "llff", "nsvf"):
+        raise NotImplementedError(f"dataset {args.dataset!r}: blender, llff or nsvf expected")
     if (args.net_depth, args.net_width, args.skip_layer, args.min_deg_point, args.max_deg_point) != (8, 256, 4, 0, 10):
         raise NotImplementedError("the fused kernel is built for the 8x256 trunk, skip 4, posenc degrees 0..10")
     if tuple(str(a).lower() for a in (args.net_activation, args.rgb_activation, args.sigma_activation)) != (
             "relu", "sigmoid", "relu"):
         raise NotImplementedError("activations other than relu / sigmoid / relu")   # models.py:280-281 raise the same
-    if args.legacy_posenc_order or args.render_path or args.spherify:
-        raise NotImplementedError("legacy_posenc_order / render_path / spherify are outside the scope of this path")
+    if args.legacy_posenc_order:
+        raise NotImplementedError("legacy_posenc_order is outside the scope of this path")
+    if (args.render_path or args.spherify) and args.dataset != "llff":
+        raise ValueError("render_path / spherify apply to the llff dataset only")        # datasets.py:194-195,496-497

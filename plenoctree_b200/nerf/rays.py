@@ -4,6 +4,7 @@ the CPU reference arm of bench.py and the oracle-side tests can use it without m
     Rays namedtuple          nerf_sh/nerf/utils.py:53
     pose_spherical           nerf_sh/nerf/utils.py:656-685
     generate_rays            nerf_sh/nerf/utils.py:545-589
+    convert_to_ndc           nerf_sh/nerf/datasets.py:40-60
 """
 import collections
 
@@ -33,6 +34,20 @@ def generate_rays(w, h, focal, camtoworlds):
     origins = np.broadcast_to(camtoworlds[:, None, None, :3, 3], dirs.shape).astype(np.float32).copy()
     viewdirs = dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)
     return Rays(origins, dirs, viewdirs.astype(np.float32))
+
+
+def convert_to_ndc(origins, directions, focal, w, h, near=1.0):
+    """Rays of a forward-facing scene in normalised device coordinates: origins moved onto the plane z = -near,
+    then the perspective projection that maps the frustum to [-1,1]^3 (z: near -> -1, infinity -> +1)."""
+    shift = -(near + origins[..., 2]) / directions[..., 2]
+    o = origins + shift[..., None] * directions
+    sx, sy = -((2 * focal) / w), -((2 * focal) / h)
+    ox_z, oy_z = o[..., 0] / o[..., 2], o[..., 1] / o[..., 2]
+    ndc_o = np.stack([sx * ox_z, sy * oy_z, 1 + 2 * near / o[..., 2]], axis=-1)
+    ndc_d = np.stack([sx * (directions[..., 0] / directions[..., 2] - ox_z),
+                      sy * (directions[..., 1] / directions[..., 2] - oy_z),
+                      -2 * near / o[..., 2]], axis=-1)
+    return ndc_o, ndc_d
 
 
 def random_rays_np(n, seed, w=800, h=800, camera_angle_x=0.6911112070083618, radius=4.0, n_poses=100, focal=None):

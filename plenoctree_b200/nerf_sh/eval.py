@@ -29,7 +29,7 @@ def main(unused_argv):
     step = checkpoints.restore_checkpoint(FLAGS.train_dir, model, state)
     if step is None:
         raise ValueError(f"no checkpoint_* in {FLAGS.train_dir}")
-    out_dir = os.path.join(FLAGS.train_dir, "test_preds")
+    out_dir = os.path.join(FLAGS.train_dir, "path_renders" if FLAGS.render_path else "test_preds")   # eval.py:63-65
     if FLAGS.save_output:
         os.makedirs(out_dir, exist_ok=True)
     psnrs, ssims = [], []
@@ -38,6 +38,11 @@ def main(unused_argv):
         if idx % FLAGS.approx_eval_skip != 0:
             continue
         pred_color, pred_disp, pred_acc = utils.render_image(model, batch["rays"], chunk=FLAGS.chunk)
+        if FLAGS.render_path:                          # generated camera path (llff): frames only, no ground truth
+            if FLAGS.save_output:
+                utils.save_img(pred_color, os.path.join(out_dir, f"{idx:03d}.png"))
+                utils.save_img(pred_disp[..., 0], os.path.join(out_dir, f"disp_{idx:03d}.png"))
+            continue
         gt = torch.from_numpy(batch["pixels"]).to(pred_color.device)
         psnr = float(utils.compute_psnr(float(((pred_color - gt) ** 2).mean())))
         ssim = float(utils.compute_ssim(pred_color, gt, max_val=1.0))
@@ -47,6 +52,8 @@ def main(unused_argv):
         if FLAGS.save_output:
             utils.save_img(pred_color, os.path.join(out_dir, f"{idx:03d}.png"))
             utils.save_img(pred_disp[..., 0], os.path.join(out_dir, f"disp_{idx:03d}.png"))
+    if FLAGS.render_path:
+        return None, None
     if FLAGS.save_output:
         for name, val in (("psnr.txt", np.mean(psnrs)), ("ssim.txt", np.mean(ssims))):
             with open(os.path.join(out_dir, name), "w") as f:

@@ -353,6 +353,92 @@ def gen_ref_loss():
     print("ref_loss.npz", {k: float(out[k]) for k in ("loss", "loss_c", "loss_sp", "weight_l2", "psnr")})
 
 
+def write_llff_scene(data_dir, images_u8, poses_bounds, factor=0):
+    """images[_<factor>]/NNN.png + poses_bounds.npy, the layout nerf_sh/nerf/datasets.py:238-266 reads."""
+    from PIL import Image
+    sub = os.path.join(data_dir, "images" + (f"_{factor}" if factor > 0 else ""))
+    os.makedirs(sub, exist_ok=True)
+    for i, im in enumerate(images_u8):
+        Image.fromarray(im, mode="RGB").save(os.path.join(sub, f"{i:03d}.png"))
+    np.save(os.path.join(data_dir, "poses_bounds.npy"), poses_bounds)
+
+
+def synthetic_llff(seed, n, h, w, focal, ring=False):
+    """n cameras in the LLFF on-disk convention ([down, right, back | t | h,w,f] + near/far bounds): forward-facing
+    around the origin looking down -z, or (ring) on a circle looking inwards."""
+    rs = np.random.RandomState(seed)
+    rows = []
+    for i in range(n):
+        if ring:
+            a = 2 * np.pi * i / n + rs.uniform(-0.1, 0.1)
+            pos = np.array([2.5 * np.cos(a), 2.5 * np.sin(a), 0.4 + rs.uniform(-0.2, 0.2)])
+            back = pos / np.linalg.norm(pos)
+            world_up = np.array([0.0, 0.0, 1.0])
+        else:
+            pos = rs.uniform(-0.6, 0.6, size=3) * np.array([1.0, 1.0, 0.2])
+            back = np.array([0.0, 0.0, 1.0]) + rs.uniform(-0.15, 0.15, size=3)
+            back /= np.linalg.norm(back)
+            world_up = np.array([0.0, 1.0, 0.0])
+        right = np.cross(world_up, back); right /= np.linalg.norm(right)
+        up = np.cross(back, right)
+        m = np.stack([-up, right, back, pos, np.array([h, w, focal], dtype=np.float64)], axis=1)      # [3,5]
+        near = rs.uniform(1.2, 2.0)
+        rows.append(np.concatenate([m.reshape(-1), [near, near * rs.uniform(4.0, 8.0)]]))
+    images = rs.randint(0, 256, size=(n, h, w, 3)).astype(np.uint8)
+    return images, np.stack(rows).astype(np.float64)
+
+
+def gen_ref_llff():
+    """Execute the reference's LLFF loader (nerf_sh/nerf/datasets.py:235-487: pose re-ordering, bound rescale,
+    recentring, spiral / spherical render paths, llffhold split, NDC rays via convert_to_ndc :40-60) unmodified on
+    synthetic scenes written to a temporary directory; jax only enters through `import jax` at module level."""
+    import tempfile
+    import types
+    import jax_stub
+    names = jax_stub.install()
+    try:
+        from nerf_sh.nerf import utils as RU            # pulls in the real nerf_sh.nerf.datasets
+        RD = sys.modules["nerf_sh.nerf.datasets"]
+        out = {}
+        cases = {"fwd": dict(seed=11, n=9, h=12, w=16, focal=20.0, ring=False, factor=0, spherify=False),
+                 "ring": dict(seed=12, n=10, h=10, w=14, focal=36.0, ring=True, factor=2, spherify=True)}
+        for name, c in cases.items():
+            images, pb = synthetic_llff(c["seed"], c["n"], c["h"], c["w"], c["focal"] * max(c["factor"], 1), c["ring"])
+            out[f"{name}_images"], out[f"{name}_poses_bounds"] = images, pb
+            with tempfile.TemporaryDirectory() as d:
+                write_llff_scene(d, images, pb, c["factor"])
+                for split in ("train", "test"):
+                    args = types.SimpleNamespace(data_dir=d, factor=c["factor"], spherify=c["spherify"], llffhold=4,
+                                                 render_path=(split == "test"))
+                    ds = RD.LLFF.__new__(RD.LLFF)          # no thread / queue: the two loader stages only
+                    ds.split = split
+                    ds._load_renderings(args)
+                    ds._generate_rays()
+                    k = f"{name}_{split}_"
+                    out[k + "images"] = np.asarray(ds.images, dtype=np.float32)
+                    out[k + "camtoworlds"] = np.asarray(ds.camtoworlds)
+                    out[k + "focal"] = np.asarray(ds.focal)
+                    out[k + "hw_n"] = np.array([ds.h, ds.w, ds.n_examples])
+                    for f, r in zip(("o", "d", "v"), ds.rays):
+                        out[k + "rays_" + f] = np.asarray(r)
+                    if split == "test":
+                        out[k + "render_poses"] = np.asarray(ds.render_poses)
+                        for f, r in zip(("o", "d", "v"), ds.render_rays):
+                            out[k + "render_rays_" + f] = np.asarray(r)[::15]        # every 15th path pose
+        # convert_to_ndc on free rays (near != 1 too)
+        rs = np.random.RandomState(5)
+        o = rs.uniform(-1, 1, size=(64, 3)).astype(np.float32)
+        dd = rs.uniform(-1, 1, size=(64, 3)).astype(np.float32); dd[:, 2] = -np.abs(dd[:, 2]) - 0.2
+        out["ndc_in_o"], out["ndc_in_d"] = o, dd
+        for near in (1.0, 0.5):
+            no, nd = RD.convert_to_ndc(o, dd, np.float32(21.5), 16, 12, near=near)
+            out[f"ndc_o_{near}"], out[f"ndc_d_{near}"] = no, nd
+        np.savez_compressed(os.path.join(HERE, "ref_llff.npz"), **out)
+        print("ref_llff.npz:", {k: v.shape for k, v in out.items() if "test_render_poses" in k or "train_rays_o" in k})
+    finally:
+        jax_stub.uninstall(names)
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -395,6 +481,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ref_loss":
         gen_ref_loss()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_llff":         # own process: imports the real loaders module
+        gen_ref_llff()
         sys.exit(0)
     gen_ref_render()
     gen_ref_loss()

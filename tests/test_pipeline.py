@@ -92,6 +92,58 @@ def test_blender_loader_cpu(tmp_path):
         assert len(json.load(f)["frames"]) == 3
 
 
+def _write_llff(d, images_u8, poses_bounds, factor):
+    from PIL import Image
+    sub = os.path.join(d, "images" + (f"_{factor}" if factor > 0 else ""))
+    os.makedirs(sub, exist_ok=True)
+    for i, im in enumerate(images_u8):
+        Image.fromarray(im, mode="RGB").save(os.path.join(sub, f"{i:03d}.png"))
+    np.save(os.path.join(d, "poses_bounds.npy"), poses_bounds)
+
+
+@pytest.mark.parametrize("case,factor,spherify", [("fwd", 0, False), ("ring", 2, True)])
+def test_llff_loader_matches_executed_reference(tmp_path, golden_dir, case, factor, spherify):
+    """LLFF loader against the reference's own (nerf_sh/nerf/datasets.py:235-487 executed by
+    tests/golden/make_golden.py ref_llff on the same synthetic scenes): recentred / spherified poses, focal, split,
+    spiral / circle render path, NDC rays of the views and of the path."""
+    from plenoctree_b200.nerf import datasets as D
+    z = np.load(os.path.join(golden_dir, "ref_llff.npz"))
+    _write_llff(str(tmp_path), z[f"{case}_images"], z[f"{case}_poses_bounds"], factor)
+    for split in ("train", "test"):
+        args = type("A", (), dict(data_dir=str(tmp_path), factor=factor, spherify=spherify, llffhold=4, batch_size=32,
+                                  image_batching=True, dataset="llff", render_path=(split == "test"), white_bkgd=False))
+        ds = D.get_dataset(split, args, device="cpu")
+        k = f"{case}_{split}_"
+        h, w, n = z[k + "hw_n"]
+        assert (ds.h, ds.w, ds.n_examples) == (h, w, n)
+        assert np.array_equal(ds.images, z[k + "images"])
+        np.testing.assert_allclose(ds.camtoworlds, z[k + "camtoworlds"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(ds.focal, z[k + "focal"], rtol=1e-7)
+        for f, r in zip("odv", ds.rays_np):
+            np.testing.assert_allclose(r, z[k + "rays_" + f], rtol=2e-5, atol=2e-6)
+        if split == "test":
+            assert ds.n_examples == 120
+            np.testing.assert_allclose(ds.render_poses, z[k + "render_poses"], rtol=0, atol=2e-6)
+            for f, r in zip("odv", ds.render_rays_np):
+                np.testing.assert_allclose(r[::15], z[k + "render_rays_" + f], rtol=2e-5, atol=2e-6)
+            b = ds.next_test()                                  # render_path: rays of the path, no pixels
+            assert set(b) == {"rays"} and b["rays"].origins.shape == (h, w, 3)
+        else:
+            b = ds.next_train()
+            assert b["pixels"].shape == (32, 3) and b["rays"].origins.shape == (32, 3)
+            if not spherify:                                    # NDC: every origin sits on the near plane z = -1
+                assert np.allclose(ds.rays_np.origins[..., 2], -1.0, atol=1e-5)
+
+
+def test_convert_to_ndc_matches_executed_reference(golden_dir):
+    from plenoctree_b200.nerf.rays import convert_to_ndc
+    z = np.load(os.path.join(golden_dir, "ref_llff.npz"))
+    for near in (1.0, 0.5):
+        o, d = convert_to_ndc(z["ndc_in_o"], z["ndc_in_d"], np.float32(21.5), 16, 12, near=near)
+        np.testing.assert_allclose(o, z[f"ndc_o_{near}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(d, z[f"ndc_d_{near}"], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
