@@ -26,7 +26,7 @@ class Dataset:
         self.device = torch.device(device)
         self.batch_size = int(args.batch_size) // world
         self.image_batching = bool(args.image_batching)
-        self.render_rays_np = None                           # LLFF test split only (datasets.py:349-355)
+        self._render_rays_np = None                          # LLFF test split only (datasets.py:349-355)
         self._load_renderings(args)
         if not hasattr(self, "n_examples"):
             self.n_examples = self.images.shape[0]
@@ -47,6 +47,14 @@ class Dataset:
 
     def _build_rays(self):
         return generate_rays(self.w, self.h, self.focal, self.camtoworlds)
+
+    @property
+    def render_rays_np(self):
+        """Rays of the generated camera path (`render_path`), [n_path,h,w,3] x3; built together with rays_np."""
+        self.rays_np
+        if self._render_rays_np is None:
+            raise ValueError("this dataset / split has no render path")
+        return self._render_rays_np
 
     def _device_pool(self):
         """pixels [n,hw,3] and Rays [n,hw,3] x3 resident in HBM (training batches are gathered on the device)."""
@@ -92,7 +100,6 @@ class Dataset:
         idx = self.it
         self.it = (self.it + 1) % self.n_examples
         if self.render_path:
-            self.rays_np
             return {"rays": Rays(*[r[idx] for r in self.render_rays_np])}
         return {"pixels": self.images[idx], "rays": Rays(*[r[idx] for r in self.rays_np])}
 
@@ -214,7 +221,7 @@ class LLFF(Dataset):
             o, dd = convert_to_ndc(rays.origins, rays.directions, self.focal, self.w, self.h)
             rays = Rays(o, dd, rays.viewdirs)
         if n_path:
-            self.render_rays_np = Rays(*[r[:n_path] for r in rays])
+            self._render_rays_np = Rays(*[r[:n_path] for r in rays])
             rays = Rays(*[r[n_path:] for r in rays])
         return rays
 

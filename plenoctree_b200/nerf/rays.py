@@ -14,15 +14,26 @@ import numpy as np
 Rays = collections.namedtuple("Rays", ("origins", "directions", "viewdirs"))
 
 
-def pose_spherical(theta, phi, radius):
-    """camera-to-world matrix looking at the origin (angles in degrees)."""
+def pose_spherical(theta, phi, radius, up_axis=0):
+    """camera-to-world matrix looking at the origin (angles in degrees).  up_axis 0 keeps the NeRF-synthetic frame
+    (z up); 1..5 re-orient the world so that -z / +y / -y / +x / -x is up (gen_video's --up_axis minus one)."""
     th, ph = np.deg2rad(theta), np.deg2rad(phi)
     trans = np.eye(4, dtype=np.float64)
     trans[2, 3] = radius
     rot_phi = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1.0]])
     rot_theta = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1.0]])
     flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]])
-    return (flip @ rot_theta @ rot_phi @ trans).astype(np.float32)
+    c2w = flip @ rot_theta @ rot_phi @ trans
+    if up_axis != 0:
+        up_dim = 2 - up_axis // 2                     # axis that becomes "up" ...
+        up = np.zeros(3)
+        up[up_dim] = -1.0 if up_axis % 2 else 1.0     # ... and its sign
+        e1 = np.zeros(3)
+        e1[1 if up_dim == 0 else 0] = 1.0
+        frame = np.eye(4)
+        frame[:3, 0], frame[:3, 1], frame[:3, 2] = e1, np.cross(up, e1), up
+        c2w = frame @ c2w
+    return c2w.astype(np.float32)
 
 
 def generate_rays(w, h, focal, camtoworlds):

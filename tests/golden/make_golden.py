@@ -433,6 +433,10 @@ def gen_ref_llff():
         for near in (1.0, 0.5):
             no, nd = RD.convert_to_ndc(o, dd, np.float32(21.5), 16, 12, near=near)
             out[f"ndc_o_{near}"], out[f"ndc_d_{near}"] = no, nd
+        # pose_spherical incl. the up-axis re-orientation gen_video uses (nerf_sh/nerf/utils.py:656-685)
+        sph = [(th, ph, rad, ua) for ua in range(6) for th, ph, rad in ((-180.0, -30.0, 4.0), (37.5, -75.0, 2.5))]
+        out["pose_sph_in"] = np.array(sph, dtype=np.float64)
+        out["pose_sph_out"] = np.stack([RU.pose_spherical(th, ph, rad, ua) for th, ph, rad, ua in sph])
         np.savez_compressed(os.path.join(HERE, "ref_llff.npz"), **out)
         print("ref_llff.npz:", {k: v.shape for k, v in out.items() if "test_render_poses" in k or "train_rays_o" in k})
     finally:

@@ -136,8 +136,10 @@ def test_llff_loader_matches_executed_reference(tmp_path, golden_dir, case, fact
 
 
 def test_convert_to_ndc_matches_executed_reference(golden_dir):
-    from plenoctree_b200.nerf.rays import convert_to_ndc
+    from plenoctree_b200.nerf.rays import convert_to_ndc, pose_spherical
     z = np.load(os.path.join(golden_dir, "ref_llff.npz"))
+    for (th, ph, rad, ua), want in zip(z["pose_sph_in"], z["pose_sph_out"]):        # all six up axes
+        np.testing.assert_allclose(pose_spherical(th, ph, rad, int(ua)), want, rtol=0, atol=1e-6)
     for near in (1.0, 0.5):
         o, d = convert_to_ndc(z["ndc_in_o"], z["ndc_in_d"], np.float32(21.5), 16, 12, near=near)
         np.testing.assert_allclose(o, z[f"ndc_o_{near}"], rtol=1e-6, atol=1e-7)
@@ -186,6 +188,10 @@ def test_cli_chain_train_eval_extract_optimize(tmp_path):
     model, state = TR.main(None)
     assert os.path.exists(os.path.join(train_dir, "checkpoint_300")) and state.step == 300
     psnr, ssim = EV.main(None)
+    from plenoctree_b200.nerf_sh import gen_video as GV                 # orbit video from the same checkpoint
+    FLAGS.num_views, FLAGS.height, FLAGS.width, FLAGS.elevation, FLAGS.radius = 3, 32, 32, -30.0, "4.0"
+    vdir = GV.main(None)
+    assert sorted(os.listdir(os.path.join(vdir, "frames"))) == ["0000.png", "0001.png", "0002.png"]
     assert os.path.exists(os.path.join(train_dir, "test_preds", "000.png"))
     assert float(open(os.path.join(train_dir, "test_preds", "psnr.txt")).read()) == pytest.approx(psnr)
     fresh = NerfModel(sh_deg=sh_deg, max_rays=4096)
@@ -319,7 +325,9 @@ def test_reference_module_paths_and_yaml(tmp_path):
     code = (
         "import sys\n"
         "from absl import flags\n"
-        "import nerf_sh.train as T, nerf_sh.eval, octree.extraction, octree.optimization, octree.evaluation\n"
+        "import nerf_sh.train as T, nerf_sh.eval, nerf_sh.gen_video as GV\n"
+        "import octree.extraction, octree.optimization, octree.evaluation\n"
+        "assert GV.orbit_poses(8, -30.0, 4.0, 3).shape == (8, 4, 4)\n"
         "from plenoctree_b200.nerf import flags as F\n"
         "assert T.main.__module__ == 'plenoctree_b200.nerf_sh.train'\n"
         f"flags.FLAGS(['prog', '--train_dir', '/tmp/x', '--data_dir', '/tmp/y', '--config', r'{cfg.with_suffix('')}', "
