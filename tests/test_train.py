@@ -181,38 +181,6 @@ def test_training_reduces_loss():
     assert np.isfinite(last.loss) and last.loss < 0.5 * first.loss, (first, last)
 
 
-def test_fused_backward_matches_classic():
-    """opt-in fused dgrad+wgrad launch (POB_FUSED_BWD=1): same gradients as the two-kernel path."""
-    import subprocess, sys
-    code = r"""
-import numpy as np, torch, sys
-sys.path.insert(0, %r)
-from tests.test_train import _setup
-from plenoctree_b200.nerf.models import NerfModel, Rays
-from plenoctree_b200.nerf import train as T
-fc, ff, rays, px, t_rand, u, sp = _setup(3, 96, 128, 300, 77)
-model = NerfModel(sh_deg=3, num_coarse_samples=64, num_fine_samples=128, max_rays=96, sparsity_npoints=300)
-model.set_params(np.concatenate([fc, ff]))
-state = T.TrainState(model)
-T.loss_and_grad(model, state, {"rays": Rays(*rays), "pixels": px}, sparsity_weight=1e-3, sparsity_length=0.05,
-                randomized=True, t_rand=t_rand, u=u, sp_points=sp)
-torch.cuda.synchronize()
-np.save(sys.argv[1], state.grads.cpu().numpy())
-""" % ROOT
-    import tempfile
-    outs = []
-    for flag in ("0", "1"):
-        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
-            env = dict(os.environ, POB_FUSED_BWD=flag)
-            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
-            outs.append(np.load(f.name))
-    a, b = outs
-    assert np.isfinite(b).all()
-    # identical operands, same fp32 MMA accumulation per tile; only the order in which tiles are summed
-    # into a consumer's accumulator differs
-    assert float(np.linalg.norm(a - b) / np.linalg.norm(a)) < 1e-4
-
-
 def test_loss_and_grad_with_sigma_noise():
     """row a4 in training: the relu mask of sigma follows the NOISED pre-activation (train.py:70 -> models.py:274)."""
     from oracle import nerf_sh_oracle as O
@@ -315,7 +283,8 @@ def test_draw_uniforms_philox():
 @pytest.mark.gpu
 def test_graphed_train_step_matches_eager():
     """GraphedTrainStep (one CUDA graph per step: Philox draws keyed by the device-side step, kernels, Adam with
-    lr / step from the device buffer) must reproduce the eager train_step sequence bit for bit."""
+    lr / step from the device buffer) must reproduce the eager train_step sequence: parameters and Adam moments bit
+    for bit, with the host queueing all replays ahead of the device (the (lr, step) staging ring is what is tested)."""
     from plenoctree_b200.nerf.models import NerfModel, Rays
     from plenoctree_b200.nerf import train as T
     R = 256
@@ -339,6 +308,8 @@ def test_graphed_train_step_matches_eager():
         torch.cuda.synchronize()
         assert state.step == len(lrs)
         outs.append((model.params.clone(), state.m.clone(), state.v.clone(), state.stats_raw.clone()))
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    for name, a, b in zip(("params", "m", "v"), *[o[:3] for o in outs]):
+        assert torch.equal(a, b), name
+    # the loss sums are float atomics over the rays (order varies from launch to launch): equal to rounding only
+    assert torch.allclose(outs[0][3], outs[1][3], rtol=1e-4, atol=1e-3)
     assert not torch.equal(outs[0][0], torch.from_numpy(np.concatenate([fc, ff])).cuda())
