@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._lib import PREC_FP16, PREC_FP16X3, RenderConfig, check, lib, ptr, stream_ptr
+from .._lib import PREC_FP16, RenderConfig, check, lib, ptr, stream_ptr
 from ..layouts import K_of
 
 from .rays import Rays  # noqa: F401  (nerf_sh/nerf/utils.py:53)

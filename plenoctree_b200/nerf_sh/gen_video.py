@@ -7,7 +7,6 @@ of each frame and rank 0 writes the files."""
 import os
 
 import numpy as np
-import torch
 from absl import app, flags
 
 from .. import _dist

@@ -13,7 +13,6 @@ returns the reference defaults.  `nerf` is plenoctree_b200.nerf.models.NerfModel
 outside the scope of this path and raise NotImplementedError.
 """
 import ctypes
-import math
 import os
 import types
 

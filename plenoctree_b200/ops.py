@@ -4,8 +4,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib
-from ._lib import PREC_FP16, PREC_FP16X3, check, lib, ptr, stream_ptr
+from ._lib import PREC_FP16, PREC_FP16X3, check, lib, ptr, stream_ptr  # noqa: F401  (precision modes re-exported)
 from .layouts import K_of
 
 
