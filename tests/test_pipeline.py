@@ -146,6 +146,62 @@ def test_convert_to_ndc_matches_executed_reference(golden_dir):
         np.testing.assert_allclose(d, z[f"ndc_d_{near}"], rtol=1e-6, atol=1e-7)
 
 
+def test_marching_tetrahedra_sphere_is_closed_oriented_manifold():
+    """nerf/mesh.py (stands in for PyMCubes in gen_mesh): on a sphere's signed distance the surface is watertight
+    (every edge in exactly two triangles, once per direction), has Euler characteristic 2, outward normals (positive
+    signed volume, within 1 % of the ball's) and vertices on the sphere to second order in the grid spacing."""
+    from plenoctree_b200.nerf.mesh import marching_tetrahedra, save_obj
+    n, r0 = 40, 0.6
+    g = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    v, f = marching_tetrahedra((r0 - np.sqrt(X * X + Y * Y + Z * Z)).astype(np.float32), 0.0)
+    w = v * (2.0 / (n - 1)) - 1.0
+    rad = np.linalg.norm(w, axis=1)
+    assert rad.max() < r0 + 1e-6 and rad.min() > r0 - (2.0 / (n - 1)) ** 2
+    d = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    fwd, rev = d[:, 0] * len(v) + d[:, 1], d[:, 1] * len(v) + d[:, 0]
+    assert len(np.unique(fwd)) == len(fwd) and np.array_equal(np.sort(fwd), np.sort(rev))
+    assert len(v) - len(fwd) // 2 + len(f) == 2
+    p0, p1, p2 = w[f[:, 0]], w[f[:, 1]], w[f[:, 2]]
+    vol = float((p0 * np.cross(p1, p2)).sum() / 6.0)
+    assert abs(vol / (4.0 / 3.0 * np.pi * r0 ** 3) - 1.0) < 0.01
+    assert marching_tetrahedra(np.zeros((4, 4, 4), np.float32), 1.0)[1].shape == (0, 3)      # nothing inside
+
+
+def test_gen_mesh_grid_and_scaling_cpu(tmp_path):
+    """gen_mesh's grid walk (points = linspace(c1, c2, reso) per axis, "ij" order, chunked) and the reference's
+    vertex scaling c1 + index * (c2 - c1) / reso (gen_mesh.py:105-129), with an analytic density in place of the MLP."""
+    from plenoctree_b200.nerf_sh import gen_mesh as GM
+    from plenoctree_b200.nerf.mesh import save_obj
+
+    class Field:
+        device = torch.device("cpu")
+        calls = 0
+
+        def eval_points_raw(self, pts, coarse=False, want_rgb=True):
+            Field.calls += 1
+            assert pts.shape[1] == 3 and not want_rgb
+            c = torch.tensor([0.2, -0.1, 0.3])
+            return None, (10.0 - 10.0 * ((pts - c) ** 2).sum(1, keepdim=True).sqrt())         # sigma = 6 at r = 0.4
+
+    reso, c1, c2 = [24, 30, 20], [-1.0, -1.5, -0.5], [1.0, 1.0, 1.5]
+    sig = GM.sigma_grid(Field(), c1, c2, reso, chunk=1000)
+    assert Field.calls == -(-24 * 30 * 20 // 1000) and sig.shape == (24, 30, 20)
+    x, y, z = np.linspace(-1, 1, 24)[5], np.linspace(-1.5, 1, 30)[17], np.linspace(-0.5, 1.5, 20)[3]
+    assert abs(sig[5, 17, 3] - (10 - 10 * np.sqrt((x - 0.2) ** 2 + (y + 0.1) ** 2 + (z - 0.3) ** 2))) < 1e-4
+    verts, faces = GM.marching_cubes(Field(), c1, c2, reso, 6.0, 5000)
+    assert len(faces) > 100
+    # the reference scales by (c2 - c1) / reso (not reso - 1): undo it to land on the sampled field's sphere
+    idx = (verts - np.array(c1)) / ((np.array(c2) - np.array(c1)) / np.array(reso))
+    world = np.array(c1) + idx * (np.array(c2) - np.array(c1)) / (np.array(reso) - 1)
+    rad = np.linalg.norm(world - np.array([0.2, -0.1, 0.3]), axis=1)
+    assert abs(rad - 0.4).max() < 0.01
+    save_obj(verts, faces, str(tmp_path / "m.obj"), vert_rgb=np.zeros_like(verts))
+    lines = open(tmp_path / "m.obj").read().splitlines()
+    assert sum(l.startswith("v ") for l in lines) == len(verts) and sum(l.startswith("f ") for l in lines) == len(faces)
+    assert len(lines[0].split()) == 7 and min(int(t) for l in lines if l.startswith("f ") for t in l.split()[1:]) == 1
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
@@ -325,7 +381,7 @@ def test_reference_module_paths_and_yaml(tmp_path):
     code = (
         "import sys\n"
         "from absl import flags\n"
-        "import nerf_sh.train as T, nerf_sh.eval, nerf_sh.gen_video as GV\n"
+        "import nerf_sh.train as T, nerf_sh.eval, nerf_sh.gen_video as GV, nerf_sh.gen_mesh\n"
         "import octree.extraction, octree.optimization, octree.evaluation\n"
         "assert GV.orbit_poses(8, -30.0, 4.0, 3).shape == (8, 4, 4)\n"
         "from plenoctree_b200.nerf import flags as F\n"
