@@ -10,12 +10,12 @@
 // products, exp, sigmoid, compositing sums) may contract to FMA and uses the fast exp / reciprocal — the march is
 // instruction-issue bound (ncu: sm__throughput 73-79 %, DRAM 5 %), so instruction count is what matters.
 //
-// Thread mapping (B200-first, not svox's thread-per-ray): a *group* of G lanes (16 for K <= 16 basis
-// functions, 32 for SH25) owns one ray.  All lanes walk the tree redundantly (same-address loads
-// broadcast), lane l owns basis function l: the 3K coefficient gather of a contributing leaf is three
-// coalesced 4K-byte segments per group instead of 3K strided scalar loads per thread, the dot products
-// finish with log2(G) shuffles, and the backward scatter issues coalesced RED.ADD.F32 (one L2 atomic
-// sector per 8 lanes).  Pixels are tiled 4x4 (4x2) per CTA so neighbouring rays share L1 lines.
+// Thread mapping (B200-first, not svox's thread-per-ray): a *group* of G lanes owns one ray (G = 4 by default,
+// see group_width(); 8 / 16 / 32 selectable for profiling).  All lanes of a group walk the tree together
+// (same-address loads broadcast), lane l owns basis functions l, l+G, ...: the 3K coefficient gather of a
+// contributing leaf is three coalesced segments per group instead of 3K strided scalar loads per thread, the dot
+// products finish with log2(G) shuffles, and the backward scatter issues coalesced RED.ADD.F32.  Pixels are tiled
+// per CTA so that neighbouring rays share L1 lines.
 #include <cstdint>
 #include <cstdlib>
 
