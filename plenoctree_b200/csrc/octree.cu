@@ -27,8 +27,10 @@ namespace pob {
 namespace {
 
 // Safety caps (never reached by a valid tree / positive step): a corrupt child array or a step that underflows
-// against t must not hang the device.
-constexpr int MAX_MARCH_STEPS = 1 << 17;
+// against t must not hang the device.  A march visits one leaf per iteration (a few thousand for a depth-10 tree);
+// the cap only has to exceed sqrt(3) / step_size for the smallest step the reference's configurations use
+// (renderer_step_size 1e-5, octree/config/syn_sh16.json:16,22,24), since every iteration advances by >= step_size.
+constexpr int MAX_MARCH_STEPS = 1 << 20;
 constexpr int MAX_TREE_DEPTH = 40;
 
 struct TreeDev {
@@ -711,8 +713,8 @@ int opts_dev(const char* where, const pob_octree_opts* o, Opts& O) {
   if (!o) return pob_fail(where, "options are NULL");
   // every march iteration advances by at least step_size (unit cube): below sqrt(3) / MAX_MARCH_STEPS a diagonal ray
   // would run into the iteration cap and composite the background through the unmarched remainder
-  if (!(o->step_size >= 1.4e-5f))
-    return pob_fail(where, "step_size must be >= 1.4e-5 (the march is capped at 131072 steps per ray)");
+  if (!(o->step_size >= 2e-6f))
+    return pob_fail(where, "step_size must be >= 2e-6 (the march is capped at 2^20 iterations per ray)");
   O.step = o->step_size;
   O.bg = o->background_brightness;
   O.sigma_thresh = o->sigma_thresh;
