@@ -202,6 +202,61 @@ def test_gen_mesh_grid_and_scaling_cpu(tmp_path):
     assert len(lines[0].split()) == 7 and min(int(t) for l in lines if l.startswith("f ") for t in l.split()[1:]) == 1
 
 
+def test_task_manager_expands_dispatches_and_records(tmp_path):
+    """octree.task_manager (octree/task_manager.py:28-195; scene-level replicas): task expansion with the "{%}" scene
+    mark, one command triple per task with the task's flags (the reference's syn_sh16.json flag set), one worker per
+    GPU id with CUDA_VISIBLE_DEVICES pinned, results.txt = capacity / raw metrics / optimised metrics."""
+    import subprocess
+    from plenoctree_b200.octree import task_manager as TM
+    spec = {"data_root": str(tmp_path / "data"), "train_root": str(tmp_path / "ckpt"),
+            "scenes": ["chair", "drums", "lego"],
+            "scene_tasks": [{"octree_name": "", "train_dir": "{%}", "data_dir": "{%}", "config": "nerf_sh/config/blender",
+                             "extr_flags": ["--autoscale", "--scale_alpha_thresh", "0.1", "--radius", "1.4",
+                                            "--samples_per_cell", "256", "--no_early_stop", "--renderer_step_size", "1e-5"],
+                             "opt_flags": ["--num_epochs", "80", "--sgd", "--lr", "1e7", "--no_early_stop",
+                                           "--renderer_step_size", "1e-5"],
+                             "eval_flags": ["--renderer_step_size", "1e-5"]}],
+            "tasks": [{"octree_name": "oct_m", "train_dir": "materials", "data_dir": "materials",
+                       "config": "nerf_sh/config/blender", "extr_flags": ["--bbox_scale", "1.1"], "opt_flags": [],
+                       "eval_flags": []}]}
+    tasks = TM.expand_tasks(spec)
+    assert [os.path.basename(t["train_dir"]) for t in tasks] == ["materials", "chair", "drums", "lego"]
+    store, cmds, raw, final = TM.commands_for(tasks[1], keep_raw=True, python="python")
+    assert store == os.path.join(spec["train_root"], "chair", "octrees", "")          # octree_name "" like the reference's
+    assert cmds["extract"][:4] == ["python", "-u", "-m", "octree.extraction"] and "--is_jaxnerf_ckpt" in cmds["extract"]
+    assert cmds["extract"][cmds["extract"].index("--output") + 1] == raw and raw.endswith("tree.npz")
+    assert cmds["optimize"][cmds["optimize"].index("--output") + 1] == final and final.endswith("tree_opt.npz")
+    assert cmds["evaluate"][cmds["evaluate"].index("--input") + 1] == final and cmds["extract"][-2:] == ["--renderer_step_size", "1e-5"]
+    assert TM.parse_capacity("x\nplenoctree_b200.N3Tree(N=2, data_dim=49, depth_limit=10, capacity:1234/2048, ...)\n") == 1234
+    assert TM.parse_metrics("foo\nAverage PSNR 31.25 SSIM 0.961\n") [:2] == (31.25, 0.961)
+    assert TM.parse_metrics("Average PSNR 30.0 SSIM 0.9 LPIPS 0.05\n") == (30.0, 0.9, 0.05) and TM.parse_metrics("nothing") is None
+    seen = []
+
+    def fake_run(argv, env=None, check=False, stdout=None, text=None):
+        seen.append((argv[3], env["CUDA_VISIBLE_DEVICES"], argv[argv.index("--data_dir") + 1]))
+        out = ""
+        if argv[3] == "octree.extraction":
+            out = "tree(capacity:77/128)\nAverage PSNR 25.5 SSIM 0.9\n"
+        elif argv[3] == "octree.optimization":
+            if "drums" not in argv[argv.index("--data_dir") + 1]:               # drums: optimisation leaves no tree
+                open(argv[argv.index("--output") + 1], "w").write("npz")
+        else:
+            out = "Average PSNR 28.5 SSIM 0.95\n"
+        return subprocess.CompletedProcess(argv, 0, stdout=out)
+
+    for t in tasks[1:]:
+        os.makedirs(t["train_dir"]); os.makedirs(t["data_dir"])
+    res = TM.run_all(tasks[1:], gpus=[3, 5], keep_raw=True, run=fake_run)
+    assert {g for _, g, _ in seen} <= {"3", "5"} and len(seen) == 3 + 2 + 3      # drums skips the evaluation
+    assert res[0]["capacity"] == 77 and res[0]["opt"][:2] == (28.5, 0.95) and res[1]["opt"] is None
+    lines = open(os.path.join(tasks[1]["train_dir"], "octrees", "results.txt")).read().split("\n")
+    assert lines[0] == "77" and lines[1].startswith("25.5000000000 0.9000000000 nan") and lines[2].startswith("28.5000000000")
+    drums = open(os.path.join(tasks[2]["train_dir"], "octrees", "results.txt")).read().split("\n")
+    assert drums[2] == drums[1]                                                   # raw metrics repeated
+    (tmp_path / "t.json").write_text(json.dumps(spec))
+    assert TM.main([str(tmp_path / "t.json"), "--gpus", "0 1", "--dry_run"]) == 0
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
