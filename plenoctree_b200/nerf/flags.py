@@ -101,8 +101,14 @@ def update_flags(args):
     if getattr(args, "config", None) is None:
         return
     pth = os.path.expanduser(args.config + ".yaml")
-    with open(pth, "r") as fin:
-        configs = yaml.load(fin, Loader=yaml.FullLoader)
+    if not os.path.exists(pth):
+        from ..presets import nerf_sh_preset          # the reference's shipped configs, by base name
+        configs = nerf_sh_preset(args.config)
+        if configs is None:
+            raise FileNotFoundError(pth)
+    else:
+        with open(pth, "r") as fin:
+            configs = yaml.load(fin, Loader=yaml.FullLoader)
     known = set(args) if hasattr(args, "__iter__") else set(dir(args))
     invalid = sorted(set(configs.keys()) - known)
     if invalid:

@@ -141,8 +141,14 @@ def main(argv=None):
     ap.add_argument("--keep_raw", action="store_true", help="do not overwrite raw octree (takes extra disk space)")
     ap.add_argument("--dry_run", action="store_true", help="print the commands of every task and exit")
     args = ap.parse_args(argv)
-    with open(args.task_json) as f:
-        spec = json.load(f)
+    if os.path.exists(args.task_json):
+        with open(args.task_json) as f:
+            spec = json.load(f)
+    else:
+        from ..presets import octree_tasks_preset        # octree/config/{syn_sh16,tt_sh25}.json by base name
+        spec = octree_tasks_preset(args.task_json)
+        if spec is None:
+            raise FileNotFoundError(args.task_json)
     tasks = expand_tasks(spec)
     print(len(tasks), "total tasks")
     if not args.dry_run:

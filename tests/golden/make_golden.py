@@ -443,6 +443,20 @@ def gen_ref_llff():
         jax_stub.uninstall(names)
 
 
+def gen_configs():
+    """The reference's shipped configuration files as parsed values (nerf_sh/config/{blender,tt}.yaml,
+    octree/config/{syn_sh16,tt_sh25}.json): plenoctree_b200/presets.py must reproduce them."""
+    import json
+    import yaml
+    out = {"nerf_sh": {}, "octree": {}}
+    for n in ("blender", "tt"):
+        out["nerf_sh"][n] = yaml.safe_load(open(os.path.join(REF, "nerf_sh", "config", n + ".yaml")))
+    for n in ("syn_sh16", "tt_sh25"):
+        out["octree"][n] = json.load(open(os.path.join(REF, "octree", "config", n + ".json")))
+    json.dump(out, open(os.path.join(HERE, "ref_configs.json"), "w"), indent=1, sort_keys=True)
+    print("ref_configs.json")
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -486,6 +500,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ref_loss":
         gen_ref_loss()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":
+        gen_configs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ref_llff":         # own process: imports the real loaders module
         gen_ref_llff()
         sys.exit(0)
@@ -498,6 +515,7 @@ if __name__ == "__main__":
     gen_ckpt_bridge()
     gen_ssim()
     gen_flags()
+    gen_configs()
     try:
         gen_rays()
     except Exception as e:  # octree/nerf/utils.py pulls optional deps

@@ -257,6 +257,43 @@ def test_task_manager_expands_dispatches_and_records(tmp_path):
     assert TM.main([str(tmp_path / "t.json"), "--gpus", "0 1", "--dry_run"]) == 0
 
 
+def test_presets_equal_reference_config_files(golden_dir, tmp_path):
+    """plenoctree_b200/presets.py stands in for nerf_sh/config/{blender,tt}.yaml and octree/config/{syn_sh16,tt_sh25}.json
+    when those files are absent (README command lines); values pinned by tests/golden/ref_configs.json, which
+    make_golden.py parsed from the reference's files.  `--config <dir>/blender` without a file selects the preset."""
+    from plenoctree_b200 import presets as P
+    from plenoctree_b200.nerf import flags as F
+    from plenoctree_b200.octree.task_manager import expand_tasks
+    ref = json.load(open(os.path.join(golden_dir, "ref_configs.json")))
+    for n in ("blender", "tt"):
+        assert P.NERF_SH[n] == ref["nerf_sh"][n]
+
+    def options(fl):
+        d, i = {}, 0
+        while i < len(fl):
+            if i + 1 < len(fl) and not fl[i + 1].startswith("--"):
+                d[fl[i]] = fl[i + 1]; i += 2
+            else:
+                d[fl[i]] = True; i += 1
+        return d
+    for n in ("syn_sh16", "tt_sh25"):
+        mine = P.octree_tasks_preset(f"octree/config/{n}.json")
+        a = sorted(expand_tasks(ref["octree"][n]), key=lambda t: t["train_dir"])
+        b = sorted(expand_tasks(mine), key=lambda t: t["train_dir"])
+        assert len(a) == len(b) and len(a) == {"syn_sh16": 8, "tt_sh25": 5}[n]
+        for x, y in zip(a, b):
+            assert all(x[k] == y[k] for k in ("train_dir", "data_dir", "octree_name", "config", "opt_flags", "eval_flags"))
+            assert options(x["extr_flags"]) == options(y["extr_flags"])
+    assert P.octree_tasks_preset("octree/config/other.json") is None
+    FLAGS = _set_flags(train_dir="/tmp/x", data_dir="/tmp/y", config=str(tmp_path / "nerf_sh" / "config" / "tt"), sh_deg=1)
+    F.update_flags(FLAGS)
+    assert (FLAGS.dataset, FLAGS.sh_deg, FLAGS.far, FLAGS.sparsity_length) == ("nsvf", 4, 4.0, 0.2)
+    FLAGS.config = str(tmp_path / "unknown")
+    with pytest.raises(FileNotFoundError):
+        F.update_flags(FLAGS)
+    _set_flags(config=None, dataset="blender", sh_deg=3, near=2.0, far=6.0, sparsity_radius=1.5, sparsity_length=0.05)
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
