@@ -294,6 +294,61 @@ def test_presets_equal_reference_config_files(golden_dir, tmp_path):
     _set_flags(config=None, dataset="blender", sh_deg=3, near=2.0, far=6.0, sparsity_radius=1.5, sparsity_length=0.05)
 
 
+def test_median_cut_and_tree_compression(tmp_path):
+    """octree.compression (octree/compression.py:39-145): balanced median cut (2^bits boxes of equal population,
+    palette = box mean, error falling with bits), the compressed npz's keys / shapes / dtypes, sigma thresholding,
+    --retain, and the CLI's skip rules.  svox's own quantiser is absent: parity unpinned (module docstring)."""
+    from plenoctree_b200.octree import compression as C
+    rs = np.random.RandomState(0)
+    pts = (rs.normal(size=(5000, 3)) * np.array([3.0, 1.0, 0.3])).astype(np.float32)
+    errs = []
+    for bits in (0, 1, 4, 8):
+        pal, idx = C.median_cut(pts, bits)
+        assert pal.shape == (1 << bits, 3) and idx.shape == (5000,) and idx.min() >= 0 and idx.max() < (1 << bits)
+        cnt = np.bincount(idx, minlength=1 << bits)
+        assert cnt.max() - cnt.min() <= bits                            # halves differ by at most one per round
+        for b in (0, (1 << bits) - 1):
+            assert np.allclose(pal[b], pts[idx == b].mean(0), atol=1e-5)
+        errs.append(float(((pts - pal[idx]) ** 2).mean()))
+    assert errs[0] > errs[1] > errs[2] > errs[3] and errs[3] < 0.02 * errs[0]
+    pal, idx = C.median_cut(pts[:1].repeat(7, 0), 3)                        # identical points: never split
+    assert set(idx.tolist()) == {0} and np.allclose(pal[0], pts[0]) and not pal[1:].any()
+    palw, idxw = C.median_cut(pts, 3, weights=rs.uniform(size=5000))
+    assert len(np.unique(idxw)) == 8
+    # ---- a small SH4 (K = 4) tree file ----
+    n_nodes, N, K = 20, 2, 4
+    data = rs.normal(size=(n_nodes, N, N, N, 3 * K + 1)).astype(np.float32)
+    data[..., -1] = rs.uniform(0, 10, size=data.shape[:-1])
+    z = dict(data=data.astype(np.float16), child=np.zeros((n_nodes, N, N, N), np.int32), parent_depth=np.zeros((n_nodes, 2), np.int32),
+             geom_resize_fact=np.float64(1.5), n_free=np.int32(0), n_internal=np.int32(n_nodes), depth_limit=np.int32(10),
+             invradius3=np.ones(3, np.float32), offset=np.zeros(3, np.float32), data_dim=np.int32(3 * K + 1), data_format="SH4")
+    c = C.compress_tree(dict(z), bits=5, sigma_thresh=2.0, retain=1)
+    assert not {"data", "parent_depth", "geom_resize_fact", "n_free", "n_internal", "depth_limit"} & set(c)
+    assert c["quant_colors"].shape == (K - 1, 32, 3) and c["quant_colors"].dtype == np.float16
+    assert c["quant_map"].shape == (K - 1, n_nodes, N, N, N) and c["quant_map"].dtype == np.uint16
+    assert c["sigma"].shape == (n_nodes, N, N, N) and c["data_retained"].shape == (1, n_nodes, N, N, N, 3)
+    sig = z["data"][..., -1].astype(np.float32)
+    assert np.array_equal(c["sigma"] == 0, sig <= 2.0) and np.array_equal(c["sigma"][sig > 2.0], sig[sig > 2.0])
+    back = C.decompress_data(c)
+    kept = sig > 2.0
+    orig = z["data"].astype(np.float32)
+    assert not back[~kept].any()
+    rgb_o = orig[kept][:, :-1].reshape(-1, 3, K)
+    rgb_b = back[kept][:, :-1].reshape(-1, 3, K)
+    assert np.abs(rgb_o[..., 0] - rgb_b[..., 0]).max() < 2e-3                       # retained basis function: fp16 copy
+    assert 0 < ((rgb_o[..., 1:] - rgb_b[..., 1:]) ** 2).mean() < 0.35 * (rgb_o[..., 1:] ** 2).mean()
+    src = tmp_path / "tree.npz"
+    np.savez(src, **z)
+    assert C.main([str(src), "--out_dir", str(tmp_path / "min"), "--bits", "6"]) == 0
+    out = np.load(tmp_path / "min" / "tree.npz")
+    assert "quant_map" in out.files and "data" not in out.files and out["quant_colors"].shape == (K, 64, 3)
+    stamp = os.path.getmtime(tmp_path / "min" / "tree.npz")
+    C.main([str(src), "--out_dir", str(tmp_path / "min")])                            # exists, no --overwrite: skipped
+    assert os.path.getmtime(tmp_path / "min" / "tree.npz") == stamp
+    C.main([str(src), "--out_dir", str(tmp_path / "raw"), "--noquant"])
+    assert "data" in np.load(tmp_path / "raw" / "tree.npz").files
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
