@@ -24,14 +24,15 @@ Stats = collections.namedtuple("Stats", ("loss", "psnr", "loss_c", "loss_sp", "p
 
 
 def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
-    """nerf_sh/nerf/utils.py:483-515."""
+    """Learning rate of `step` (nerf_sh/nerf/utils.py:483-515): geometric interpolation from lr_init (step 0) to
+    lr_final (step >= max_steps), times a warm-up factor that rises from lr_delay_mult to 1 along a quarter sine
+    over the first lr_delay_steps steps."""
+    frac = min(max(step / max_steps, 0.0), 1.0)
+    lr = math.exp((1.0 - frac) * math.log(lr_init) + frac * math.log(lr_final))
     if lr_delay_steps > 0:
-        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
-    else:
-        delay_rate = 1.0
-    t = np.clip(step / max_steps, 0, 1)
-    log_lerp = np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
-    return delay_rate * log_lerp
+        ramp = math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+        lr *= lr_delay_mult + (1.0 - lr_delay_mult) * ramp
+    return lr
 
 
 class TrainState:

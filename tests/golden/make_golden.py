@@ -437,6 +437,11 @@ def gen_ref_llff():
         sph = [(th, ph, rad, ua) for ua in range(6) for th, ph, rad in ((-180.0, -30.0, 4.0), (37.5, -75.0, 2.5))]
         out["pose_sph_in"] = np.array(sph, dtype=np.float64)
         out["pose_sph_out"] = np.stack([RU.pose_spherical(th, ph, rad, ua) for th, ph, rad, ua in sph])
+        # learning-rate schedule (nerf_sh/nerf/utils.py:483-515), with and without the warm-up
+        lr_in = [(s_, 5e-4, 5e-6, 2000000, d_, m_) for s_ in (0, 1, 999, 250000, 1999999, 2000000, 3000000)
+                 for d_, m_ in ((0, 1.0), (2500, 0.01))]
+        out["lr_in"] = np.array(lr_in, dtype=np.float64)
+        out["lr_out"] = np.array([float(RU.learning_rate_decay(*a)) for a in lr_in], dtype=np.float64)
         np.savez_compressed(os.path.join(HERE, "ref_llff.npz"), **out)
         print("ref_llff.npz:", {k: v.shape for k, v in out.items() if "test_render_poses" in k or "train_rays_o" in k})
     finally:

@@ -135,9 +135,14 @@ def test_llff_loader_matches_executed_reference(tmp_path, golden_dir, case, fact
                 assert np.allclose(ds.rays_np.origins[..., 2], -1.0, atol=1e-5)
 
 
-def test_convert_to_ndc_matches_executed_reference(golden_dir):
+def test_host_helpers_match_executed_reference(golden_dir):
     from plenoctree_b200.nerf.rays import convert_to_ndc, pose_spherical
     z = np.load(os.path.join(golden_dir, "ref_llff.npz"))
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.nerf.train import learning_rate_decay
+    for a, want in zip(z["lr_in"], z["lr_out"]):                                    # executed reference schedule
+        args = (a[0], a[1], a[2], a[3], int(a[4]), a[5])
+        assert abs(learning_rate_decay(*args) - want) <= 1e-12 * want and abs(O.learning_rate_decay(*args) - want) <= 1e-12 * want
     for (th, ph, rad, ua), want in zip(z["pose_sph_in"], z["pose_sph_out"]):        # all six up axes
         np.testing.assert_allclose(pose_spherical(th, ph, rad, int(ua)), want, rtol=0, atol=1e-6)
     for near in (1.0, 0.5):
