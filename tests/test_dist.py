@@ -24,6 +24,29 @@ def _worker(rank, world, port, q):
         ok = ok and (hi - lo == 2048) and lo == rank * 2048
         x0, nx = grid_slab(512, rank, world)
         ok = ok and (x0, nx) == (rank * 256, 256)
+        # octree gradient exchange (C5): the touched-row (sparse) exchange must give the dense all-reduce's sums
+        from plenoctree_b200.octree.optimization import exchange_gradients
+
+        class FakeTree:
+            n_internal = 40
+
+            def __init__(self, seed):
+                gen = torch.Generator().manual_seed(seed)
+                self.g = torch.zeros(48, 2, 2, 2, 5)
+                rows = torch.randperm(40 * 8, generator=gen)[:60 + 30 * seed]        # rank-dependent touched rows
+                self.g.view(-1, 5)[rows] = torch.randn(rows.numel(), 5, generator=gen)
+
+            def grad_buffer(self):
+                return self.g
+        want = FakeTree(0).g[:40] + FakeTree(1).g[:40]
+        for sparse in (False, True):
+            t = FakeTree(rank)
+            info = exchange_gradients(t, sparse=sparse)
+            ok = ok and info["mode"] == ("sparse" if sparse else "dense") and torch.allclose(t.g[:40], want, atol=1e-6)
+            ok = ok and not t.g[40:].any()
+        empty = FakeTree(rank)
+        empty.g.zero_()
+        ok = ok and exchange_gradients(empty, sparse=True)["bytes_per_rank"] == 0
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
