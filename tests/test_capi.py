@@ -26,6 +26,43 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert s in syms, f"{s} bound in _lib.py but not declared in the header"
 
 
+def _header_prototypes():
+    """{name: [parameter declarations]} of every `int|int64_t|const char* pob_*(...)` prototype in the header."""
+    src = open(os.path.join(ROOT, "include", "plenoctree_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for m in re.finditer(r"\b(pob_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every binding has as many arguments as the prototype, pointers bound as pointers, floats as c_float,
+    64-bit integers as 64-bit — a drifted signature would pass garbage through the ABI without any error."""
+    import ctypes as C
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for decl, ct in zip(params, argtypes):
+            is_ptr_ct = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or (isinstance(ct, type) and issubclass(ct, C._Pointer))
+            if "*" in decl or "[" in decl:                       # `const float offset[3]` decays to a pointer
+                assert is_ptr_ct, (name, decl, ct)
+            elif re.match(r"(const\s+)?float\b", decl):
+                assert ct is C.c_float, (name, decl, ct)
+            elif re.match(r"(const\s+)?double\b", decl):
+                assert ct is C.c_double, (name, decl, ct)
+            elif re.match(r"(const\s+)?(u?int64_t|long long|unsigned long long|size_t)\b", decl):
+                assert C.sizeof(ct) == 8 and not is_ptr_ct, (name, decl, ct)
+            elif re.match(r"(const\s+)?(int|unsigned|int32_t|uint32_t)\b", decl):
+                assert C.sizeof(ct) == 4, (name, decl, ct)
+            else:
+                raise AssertionError(f"{name}: unclassified parameter {decl!r}")
+
+
 def test_param_and_blob_sizes():
     assert _lib.lib.pob_abi_version() >= 1
     assert _lib.lib.pob_param_count(3) == 505649
