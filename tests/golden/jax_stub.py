@@ -38,8 +38,10 @@ def _make_jnp():
     for name in ("linspace", "concatenate", "broadcast_to", "array", "reshape", "sin", "cos", "stack", "exp",
                  "ones_like", "zeros_like", "cumprod", "cumsum", "where", "sum", "maximum", "minimum", "zeros", "ones",
                  "max", "min", "clip", "nan_to_num", "sort", "tile", "prod", "mean", "sqrt", "log", "abs", "arange",
-                 "expand_dims", "squeeze", "transpose", "matmul", "dot", "square", "power"):
+                 "expand_dims", "squeeze", "transpose", "matmul", "dot", "square", "power", "sign"):
         setattr(jnp, name, _wrap(getattr(np, name)))
+    # jnp reductions accept a list of axes; numpy wants a tuple
+    jnp.mean = _wrap(lambda x, axis=None, **k: np.mean(x, axis=tuple(axis) if isinstance(axis, list) else axis, **k))
     jnp.pi = np.pi
     jnp.float32 = np.float32
     jnp.finfo = np.finfo
@@ -189,6 +191,16 @@ def install():
     cfg_mod = types.ModuleType("jax.config")
     jax.dlpack = types.ModuleType("jax.dlpack")
     jax.scipy = types.ModuleType("jax.scipy")
+    import scipy.signal as _ss
+    jax.scipy.signal = types.SimpleNamespace(convolve2d=_wrap(lambda a, b, mode="full": _ss.convolve2d(a, b, mode=mode)))
+
+    def vmap(fn, in_axes=0, out_axes=0):
+        """jax.vmap for one array argument: apply fn to every slice along in_axes, stack along out_axes."""
+        def g(x):
+            xs = np.moveaxis(np.asarray(x), in_axes, 0)
+            return np.moveaxis(np.stack([fn(v) for v in xs], axis=0), 0, out_axes)
+        return g
+    jax.vmap = vmap
     jax.host_id = lambda: 0
     jax.host_count = lambda: 1
     jax.local_device_count = lambda: 1

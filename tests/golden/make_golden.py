@@ -437,6 +437,11 @@ def gen_ref_llff():
         sph = [(th, ph, rad, ua) for ua in range(6) for th, ph, rad in ((-180.0, -30.0, 4.0), (37.5, -75.0, 2.5))]
         out["pose_sph_in"] = np.array(sph, dtype=np.float64)
         out["pose_sph_out"] = np.stack([RU.pose_spherical(th, ph, rad, ua) for th, ph, rad, ua in sph])
+        # the JAX-side compute_ssim (nerf_sh/nerf/utils.py:396-466, "valid" borders; what nerf_sh.train / eval report) on
+        # the image pair of ssim.npz; convolve2d = scipy's, vmap = a slice loop
+        zs = np.load(os.path.join(HERE, "ssim.npz"))
+        out["ssim_jax_valid"] = np.asarray(RU.compute_ssim(zs["a"], zs["b"], 1.0), dtype=np.float64)
+        out["ssim_jax_valid_map"] = np.asarray(RU.compute_ssim(zs["a"], zs["b"], 1.0, return_map=True))
         # learning-rate schedule (nerf_sh/nerf/utils.py:483-515), with and without the warm-up
         lr_in = [(s_, 5e-4, 5e-6, 2000000, d_, m_) for s_ in (0, 1, 999, 250000, 1999999, 2000000, 3000000)
                  for d_, m_ in ((0, 1.0), (2500, 0.01))]

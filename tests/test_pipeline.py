@@ -67,6 +67,12 @@ def test_ssim_matches_reference_torch_twin(golden_dir):
     from plenoctree_b200.nerf.utils import compute_ssim
     z = np.load(os.path.join(golden_dir, "ssim.npz"))
     assert abs(float(compute_ssim(z["a"], z["b"], padding="same")) - float(z["ssim"])) < 1e-6
+    # the JAX-side function ("valid" borders, nerf_sh/nerf/utils.py:396-466) executed over the numpy stand-ins
+    zj = np.load(os.path.join(golden_dir, "ref_llff.npz"))
+    assert abs(float(compute_ssim(z["a"], z["b"], padding="valid")) - float(zj["ssim_jax_valid"])) < 2e-6
+    got_map = compute_ssim(z["a"], z["b"], padding="valid", return_map=True)
+    got_map = got_map.cpu().numpy() if hasattr(got_map, "cpu") else np.asarray(got_map)
+    assert got_map.shape == zj["ssim_jax_valid_map"].shape and np.abs(got_map - zj["ssim_jax_valid_map"]).max() < 2e-5
     same = float(compute_ssim(z["a"], z["a"]))
     assert abs(same - 1.0) < 1e-6
     assert float(compute_ssim(z["a"], z["b"])) < 1.0        # "valid" borders (JAX side)
