@@ -110,8 +110,15 @@ def auto_scale(args, center, radius, nerf):
     scale = 0.5 / radius
     offset = 0.5 * (1.0 - center / radius)
     sigmas = _grid_sigmas(nerf, reso, offset.tolist(), scale.tolist())
+    return _bbox_of_dense(sigmas, args.scale_alpha_thresh, reso, offset, scale)
+
+
+def _bbox_of_dense(sigmas, alpha_thresh, reso, offset, scale):
+    """centre and half-extent of the box around the voxel centres whose sigma reaches the alpha threshold, grown by
+    half a grid step (extraction.py:276-286: the margin is 0.5 / reso in WORLD units, as in the reference).
+    sigmas: [reso^3] x-major; offset / scale: the grid's world -> [0,1]^3 transform (torch float32 [3])."""
     approx_delta = 2.0 / reso
-    sigma_thresh = -np.log(1.0 - args.scale_alpha_thresh) / approx_delta
+    sigma_thresh = -np.log(1.0 - alpha_thresh) / approx_delta
     mask = (sigmas >= sigma_thresh).reshape(reso, reso, reso)
     xx, yy, zz = _axes(reso, offset.to(sigmas.device), scale.to(sigmas.device), sigmas.device)
     lc, uc = [], []

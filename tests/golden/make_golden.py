@@ -43,7 +43,18 @@ def load_ref_module(name, relpath):
     return mod
 
 
+def _use_reference_octree():
+    """`octree` / `nerf_sh` must resolve to the reference's packages, not to this repo's drop-in shims of the same
+    names: take the repo root off sys.path (the oracle is imported already) and forget the shims."""
+    while ROOT in sys.path:
+        sys.path.remove(ROOT)
+    for name in [m for m in sys.modules if m == "octree" or m.startswith("octree.")]:
+        if not getattr(sys.modules[name], "__file__", None) or not str(sys.modules[name].__file__).startswith(REF):
+            del sys.modules[name]
+
+
 def ref_model(sh_deg, flat_c, flat_f):
+    _use_reference_octree()
     from octree.nerf import models as ref_models
     K = (sh_deg + 1) ** 2
     model = ref_models.NerfModel(use_viewdirs=False, sh_deg=sh_deg, num_rgb_channels=3 * K,
@@ -467,6 +478,118 @@ def gen_configs():
     print("ref_configs.json")
 
 
+def gen_ref_extraction():
+    """Execute the reference's own extraction control flow — octree/extraction.py `auto_scale` (:244-286), `step1`
+    (:288-353, sigma mask) and `step2` (:355-394) plus the tail of `main` (:503-504: relu on sigma, shrink) —
+    unmodified, on the CPU, with (a) the reference's torch NerfModel twin holding seeded weights and (b) a stand-in
+    for the absent third-party `svox` package whose N3Tree is backed by oracle/octree_oracle.py (so the tree
+    internals are the oracle's; what is pinned is the reference's SEQUENCE: grid construction, thresholds, the
+    refinement schedule, leaf selection / chunking, sample -> eval -> mean -> assign, relu).  `.cuda()` is the
+    identity here; the uniforms `sample` draws are recorded."""
+    import types
+    from oracle import octree_oracle as OO
+    draws = []
+    rs = np.random.RandomState(4242)
+
+    class Format:
+        RGBA = 0
+        SH = 1
+
+        def __init__(self, name):
+            self.format = Format.RGBA if name in (None, "RGBA") else Format.SH
+            self.name = name
+
+    class View:
+        def __init__(self, tree, key):
+            self.tree, self.key = tree, key
+
+        def refine(self):
+            return self.tree.o.refine_at(self.key.numpy().astype(np.float32))
+
+        def sample(self, n):
+            lv = self.tree.o.leaves()[self.key.numpy()]
+            u = rs.uniform(size=(lv.shape[0], n, 3)).astype(np.float32)
+            draws.append(u)
+            return torch.from_numpy(self.tree.o.sample(lv, n, u))
+
+        def relu_(self):           # tree[:, -1:].relu_(): last channel of every leaf
+            o = self.tree.o
+            lv = o.leaves()
+            vals = o.data[lv[:, 0], lv[:, 1], lv[:, 2], lv[:, 3], -1]
+            o.data[lv[:, 0], lv[:, 1], lv[:, 2], lv[:, 3], -1] = np.maximum(vals, 0.0)
+
+    class N3Tree:
+        def __init__(self, N=2, data_dim=4, init_refine=0, init_reserve=1, geom_resize_fact=1.0, depth_limit=10,
+                     radius=0.5, center=(0.5, 0.5, 0.5), data_format=None, extra_data=None, map_location="cpu"):
+            self.o = OO.N3Tree(N=N, data_dim=data_dim, depth_limit=depth_limit, init_reserve=init_reserve,
+                               geom_resize_fact=geom_resize_fact, radius=radius, center=center, data_format=data_format)
+            self.data_dim = data_dim
+            self.data_format = Format(data_format)
+
+        offset = property(lambda self: torch.from_numpy(self.o.offset))
+        invradius = property(lambda self: torch.from_numpy(self.o.invradius))
+        max_depth = property(lambda self: self.o.max_depth)
+        depths = property(lambda self: torch.from_numpy(self.o.leaf_depths(self.o.leaves()).astype(np.int64)))
+
+        def __getitem__(self, key):
+            if isinstance(key, tuple):
+                assert key == (slice(None), slice(-1, None))
+                return View(self, None)
+            return View(self, key)
+
+        def __setitem__(self, key, value):
+            lv = self.o.leaves()[key.numpy()]
+            self.o.data[lv[:, 0], lv[:, 1], lv[:, 2], lv[:, 3]] = value.numpy()
+
+        def shrink_to_fit(self):
+            self.o.shrink_to_fit()
+
+        def __repr__(self):
+            return f"svox-stand-in N3Tree(nodes={self.o.n_internal})"
+
+    svox = types.ModuleType("svox")
+    svox.N3Tree, svox.NDCConfig, svox.VolumeRenderer = N3Tree, object, object
+    helpers = types.ModuleType("svox.helpers")
+    helpers._get_c_extension = lambda: types.SimpleNamespace()
+    svox.helpers = helpers
+    sys.modules["svox"], sys.modules["svox.helpers"] = svox, helpers
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.empty_cache = lambda: None
+    _use_reference_octree()
+    from octree import extraction as RE
+    RE.FLAGS(["make_golden"])
+    RE.FLAGS.masking_mode = "sigma"
+    sh_deg, L, S = 3, 3, 4
+    seed = 31337
+    flat_c = O.init_flat_params(sh_deg, seed, bias_scale=0.05)
+    flat_f = O.init_flat_params(sh_deg, seed + 1, bias_scale=0.05)
+    nerf = ref_model(sh_deg, flat_c, flat_f)
+    center, radius = [0.1, -0.05, 0.0], [1.2, 1.0, 1.1]
+    args = types.SimpleNamespace(init_grid_depth=L, alpha_thresh=0.0485, scale_alpha_thresh=0.1, chunk=1000, z_min=None,
+                                 z_max=None, samples_per_cell=S, use_viewdirs=False, projection_samples=10000,
+                                 sh_deg=sh_deg)
+    with torch.no_grad():
+        as_center, as_radius = RE.auto_scale(args, center, radius, nerf)
+        tree = N3Tree(N=2, data_dim=49, init_refine=0, init_reserve=64, geom_resize_fact=1.0, depth_limit=L,
+                      radius=radius, center=center, data_format="SH16", extra_data=None, map_location="cpu")
+        RE.step1(args, tree, nerf, None)
+        n_after_step1 = tree.o.n_internal
+        RE.step2(args, tree, nerf)
+        tree[:, -1:].relu_()
+        tree.shrink_to_fit()
+    o = tree.o
+    np.savez_compressed(os.path.join(HERE, "ref_extraction.npz"), sh_deg=sh_deg, seed=seed, init_grid_depth=L,
+                        samples_per_cell=S, chunk=args.chunk, alpha_thresh=args.alpha_thresh,
+                        scale_alpha_thresh=args.scale_alpha_thresh, center=np.array(center), radius=np.array(radius),
+                        autoscale_center=np.array(as_center), autoscale_radius=np.array(as_radius),
+                        child=o.child, parent_depth=o.parent_depth, n_internal=o.n_internal,
+                        n_after_step1=n_after_step1, data=o.data.astype(np.float32),
+                        uniforms=np.concatenate(draws, axis=0),
+                        flat_c_checksum=np.float64(flat_c.astype(np.float64).sum()))
+    print("ref_extraction.npz nodes", o.n_internal, "leaves at max depth", int((tree.depths == L).sum()),
+          "sample chunks", len(draws), "autoscale", as_center, as_radius)
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -509,6 +632,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ref_loss":
         gen_ref_loss()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_extraction":    # own process: defines the octree-side flags, patches .cuda()
+        gen_ref_extraction()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "configs":
         gen_configs()

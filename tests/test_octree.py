@@ -220,6 +220,64 @@ def to_device_tree(otree):
     return t
 
 
+def test_extraction_sequence_matches_executed_reference(golden_dir):
+    """octree/extraction.py's own control flow — auto_scale, step1 (sigma mask), step2, relu — was EXECUTED
+    (tests/golden/make_golden.py ref_extraction) with the reference's torch NeRF-SH twin and an svox stand-in
+    backed by this oracle's N3Tree.  The oracle pieces the GPU tests use as the expected value
+    (`build_tree_from_grid`, leaf order, `sample`, the cell mean + relu) must reproduce that run: same topology,
+    same leaf data; the package's bounding-box helper must reproduce auto_scale."""
+    import torch
+    from oracle import nerf_sh_oracle as O
+    from plenoctree_b200.octree import extraction as E
+    z = np.load(os.path.join(golden_dir, "ref_extraction.npz"))
+    sh_deg, L, S = int(z["sh_deg"]), int(z["init_grid_depth"]), int(z["samples_per_cell"])
+    flat_f = O.init_flat_params(sh_deg, int(z["seed"]) + 1, bias_scale=0.05)            # fine MLP: what eval_points_raw uses
+    assert abs(float(O.init_flat_params(sh_deg, int(z["seed"]), bias_scale=0.05).astype(np.float64).sum())
+               - float(z["flat_c_checksum"])) < 1e-6
+    params = O.unflatten(flat_f, sh_deg)
+    center, radius = z["center"].astype(np.float32), z["radius"].astype(np.float32)
+
+    def sigma_grid(reso, off, inv):
+        arr = ((np.arange(reso, dtype=np.float32) + np.float32(0.5)) / np.float32(reso)).astype(np.float32)
+        ax = [((arr - off[a]) / inv[a]).astype(np.float32) for a in range(3)]
+        pts = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1).reshape(-1, 3)
+        with torch.no_grad():
+            return O.eval_points_raw(params, torch.from_numpy(pts))[1].numpy().reshape(-1)
+    # ---- auto_scale (reso = 2^L) through the package's helper ----
+    inv = (np.float32(0.5) / radius).astype(np.float32)
+    off = (np.float32(0.5) * (np.float32(1.0) - center / radius)).astype(np.float32)
+    sig0 = sigma_grid(2 ** L, off, inv)
+    c, r = E._bbox_of_dense(torch.from_numpy(sig0), float(z["scale_alpha_thresh"]), 2 ** L, torch.from_numpy(off),
+                            torch.from_numpy(inv))
+    assert np.allclose(c, z["autoscale_center"], atol=1e-6) and np.allclose(r, z["autoscale_radius"], atol=1e-6)
+    assert not np.allclose(r, radius)                                                   # the box did shrink
+    # ---- step 1: topology ----
+    reso = 2 ** (L + 1)
+    sig = sigma_grid(reso, off, inv)
+    thresh = -np.log(1.0 - float(z["alpha_thresh"])) / (2.0 / reso)
+    assert np.abs(sig - thresh).min() > 1e-4                 # no voxel close enough to the threshold to flip
+    mask = sig >= thresh
+    tree, _ = OO.build_tree_from_grid(mask, L, radius, center, 3 * (sh_deg + 1) ** 2 + 1, "SH16")
+    n = int(z["n_internal"])
+    assert tree.n_internal == n == int(z["n_after_step1"]) and 0.2 < mask.mean() < 0.5
+    assert np.array_equal(tree.child[:n], z["child"]) and np.array_equal(tree.parent_depth[:n], z["parent_depth"])
+    # ---- step 2: leaves at max depth in leaf order, S samples each (the recorded uniforms), mean, relu on sigma ----
+    lv = tree.leaves()
+    deep = np.nonzero(tree.leaf_depths(lv) == L)[0]
+    assert z["uniforms"].shape == (deep.size, S, 3)
+    pts = tree.sample(lv[deep], S, z["uniforms"]).reshape(-1, 3)
+    with torch.no_grad():
+        rgb, s = O.eval_points_raw(params, torch.from_numpy(pts))
+    want = torch.cat([rgb, s], dim=-1).reshape(-1, S, tree.data_dim).mean(dim=1).numpy()
+    want[:, -1] = np.maximum(want[:, -1], 0.0)
+    ref = z["data"].reshape(-1, tree.data_dim)
+    at = tree.pack_index(lv[deep, 0], lv[deep, 1:])
+    assert np.abs(ref[at] - want).max() < 2e-5 * np.abs(want).max()
+    rest = np.ones(ref.shape[0], dtype=bool)
+    rest[at] = False
+    assert not ref[rest].any()                                # coarser leaves and internal cells stay empty
+
+
 @pytest.mark.gpu
 def test_query_and_tree_build_bit_exact():
     import torch
