@@ -590,6 +590,144 @@ def gen_ref_extraction():
           "sample chunks", len(draws), "autoscale", as_center, as_radius)
 
 
+def synthetic_octree(seed=77, data_dim=13, data_format="SH4"):
+    """a small depth-2 oracle tree (root refined, three of its cells refined again) with random leaf data:
+    SH coefficients ~ N(0, 1), densities in [0, 12)."""
+    from oracle import octree_oracle as OO
+    rs = np.random.RandomState(seed)
+    tree = OO.N3Tree(N=2, data_dim=data_dim, depth_limit=4, init_reserve=16, geom_resize_fact=1.5, radius=1.0,
+                     center=[0.0, 0.0, 0.0], data_format=data_format)
+    tree.refine_at(np.array([[0.5, 0.5, 0.5]], dtype=np.float32))
+    tree.refine_at(np.array([[0.5, 0.5, 0.5], [-0.5, 0.5, -0.5], [0.5, -0.5, 0.5]], dtype=np.float32))
+    n = tree.n_internal
+    tree.data[:n] = rs.normal(size=tree.data[:n].shape).astype(np.float32)
+    tree.data[:n, ..., -1] = rs.uniform(0.0, 12.0, size=tree.data[:n, ..., -1].shape).astype(np.float32)
+    return tree
+
+
+def gen_ref_optimization():
+    """Execute the reference's octree/optimization.py `main` (:133-248) unmodified on the CPU: Blender loader of the
+    octree side, per-image render -> clamp -> MSE -> backward -> torch.optim.SGD step, validation PSNR every epoch,
+    best-model bookkeeping and save.  `svox` is a stand-in: N3Tree = an nn.Module holding the oracle tree's arrays
+    (`data` is the Parameter SGD updates), VolumeRenderer.render_persp = an autograd Function around the oracle's
+    forward / backward march.  The renderer internals are therefore the oracle's; what is pinned is the reference's
+    training-step semantics around it (clamp gradient, mean normalisation, update order, PSNR, best-of-validation)."""
+    import contextlib
+    import copy
+    import io
+    import json
+    import tempfile
+    import types
+    from PIL import Image
+    from oracle import octree_oracle as OO
+    H = W = 6
+    focal_angle = 0.9
+    focal = 0.5 * W / np.tan(0.5 * focal_angle)
+    step_size = 1e-3
+    teacher = synthetic_octree(77)
+    student = synthetic_octree(77)
+    rs = np.random.RandomState(5)
+    n = student.n_internal
+    student.data[:n] = (student.data[:n] + rs.normal(scale=0.3, size=student.data[:n].shape)).astype(np.float32)
+    student.data[:n, ..., -1] = np.maximum(student.data[:n, ..., -1], 0.0)
+    poses = {"train": [O.pose_spherical(40.0 * i - 60.0, -30.0, 3.0) for i in range(3)],
+             "val": [O.pose_spherical(25.0, -20.0, 3.0), O.pose_spherical(-110.0, -45.0, 3.0)]}
+
+    class TreeModule(torch.nn.Module):
+        def __init__(self, o):
+            super().__init__()
+            self.o = o
+            self.data = torch.nn.Parameter(torch.from_numpy(o.data[:o.n_internal].copy()))
+
+        @classmethod
+        def load(cls, path, map_location="cpu"):
+            z = np.load(path)
+            o = OO.N3Tree(N=2, data_dim=int(z["data_dim"]), depth_limit=int(z["depth_limit"]), init_reserve=int(z["n_internal"]),
+                          geom_resize_fact=float(z["geom_resize_fact"]), data_format=str(z["data_format"]))
+            o.invradius, o.offset = z["invradius3"].astype(np.float32), z["offset"].astype(np.float32)
+            o.child, o.parent_depth = z["child"].copy(), z["parent_depth"].copy()
+            o.data = z["data"].astype(np.float32)
+            o.n_internal = int(z["n_internal"])
+            return cls(o)
+
+        def clone(self, device="cpu"):
+            c = TreeModule(copy.deepcopy(self.o))
+            c.data = torch.nn.Parameter(self.data.detach().clone())
+            return c
+
+        def save(self, path, compress=False):
+            self.o.data = self.data.detach().numpy().copy()
+            st = self.o.state()
+            st["data"] = self.o.data[:self.o.n_internal].astype(np.float32)          # keep fp32 for the comparison
+            np.savez(path, **st)
+
+    class March(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, data, tree, rays):
+            tree.o.data = data.detach().numpy().copy()
+            ctx.tree, ctx.rays = tree, rays
+            return torch.from_numpy(OO.volume_render(tree.o, *rays, step_size=step_size))
+
+        @staticmethod
+        def backward(ctx, g):
+            grad = OO.volume_render_backward(ctx.tree.o, *ctx.rays, g.numpy().astype(np.float32), step_size=step_size)
+            return torch.from_numpy(grad), None, None
+
+    class VolumeRenderer:
+        def __init__(self, tree, step_size=1e-3, ndc=None):
+            assert ndc is None
+            self.tree = tree
+
+        def render_persp(self, c2w, height, width, fx, fast=False, cuda=True):
+            assert not fast
+            rays = OO.persp_rays(c2w.numpy(), width, height, fx)
+            return March.apply(self.tree.data, self.tree, rays).reshape(height, width, 3)
+
+    svox = types.ModuleType("svox")
+    svox.N3Tree, svox.VolumeRenderer, svox.NDCConfig = TreeModule, VolumeRenderer, object
+    sys.modules["svox"] = svox
+    sys.modules["imageio"] = types.SimpleNamespace(imwrite=lambda *a, **k: None)
+    _use_reference_octree()
+    from octree import optimization as RO
+    with tempfile.TemporaryDirectory() as d:
+        gts = {}
+        for split, ps in poses.items():
+            os.makedirs(os.path.join(d, split))
+            frames = []
+            for i, c2w in enumerate(ps):
+                im = OO.volume_render(teacher, *OO.persp_rays(c2w, W, H, focal), step_size=step_size).reshape(H, W, 3)
+                rgba = np.concatenate([np.clip(im, 0, 1), np.ones((H, W, 1), np.float32)], axis=-1)
+                Image.fromarray((rgba * 255.0 + 0.5).astype(np.uint8), mode="RGBA").save(os.path.join(d, split, f"r_{i}.png"))
+                frames.append({"file_path": f"./{split}/r_{i}", "transform_matrix": np.asarray(c2w, dtype=np.float64).tolist()})
+            json.dump({"camera_angle_x": focal_angle, "frames": frames}, open(os.path.join(d, f"transforms_{split}.json"), "w"))
+        st = student.state()
+        st["data"] = student.data[:student.n_internal].astype(np.float32)
+        np.savez(os.path.join(d, "tree.npz"), **st)
+        lr = 40.0
+        open(os.path.join(d, "cfg.yaml"), "w").write("dataset: blender\nfactor: 0\nwhite_bkgd: true\n")
+        RO.FLAGS(["make_golden", "--config", os.path.join(d, "cfg"), "--input", os.path.join(d, "tree.npz"), "--output", os.path.join(d, "tree_opt.npz"),
+                  "--data_dir", d, "--dataset", "blender", "--factor", "0", "--white_bkgd", "--num_epochs", "3",
+                  "--val_interval", "1", "--sgd", "--lr", str(lr), "--continue_on_decrease", "--renderer_step_size", str(step_size)])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            RO.main(None)
+        log = buf.getvalue()
+        out = np.load(os.path.join(d, "tree_opt.npz"))
+        train_psnr = [float(l.split()[-1]) for l in log.splitlines() if l.startswith("** train_psnr")]
+        val_psnr = [float(l.split()[3]) for l in log.splitlines() if l.startswith("** val psnr")]
+        init_val = [float(l.split()[-1]) for l in log.splitlines() if l.startswith("** initial val psnr")][0]
+        ds = {s_: RO.datasets.get_dataset(s_, RO.FLAGS) for s_ in ("train", "val")}
+        np.savez_compressed(os.path.join(HERE, "ref_optimization.npz"), H=H, W=W, focal=np.float64(ds["train"].focal),
+                            step_size=step_size, lr=lr, epochs=3,
+                            train_c2w=ds["train"].camtoworlds, val_c2w=ds["val"].camtoworlds,
+                            train_gt=ds["train"].images.astype(np.float32), val_gt=ds["val"].images.astype(np.float32),
+                            child=student.child[:n], parent_depth=student.parent_depth[:n],
+                            data0=student.data[:n].astype(np.float32), invradius=student.invradius, offset=student.offset,
+                            train_psnr=np.array(train_psnr), val_psnr=np.array(val_psnr), initial_val_psnr=init_val,
+                            data_best=out["data"].astype(np.float32))
+    print("ref_optimization.npz", "initial val", init_val, "train", train_psnr, "val", val_psnr)
+
+
 def gen_ssim():
     """reference torch twin octree/nerf/utils.py::compute_ssim on two random images."""
     ref_utils = load_ref_module("ref_octree_utils2", "octree/nerf/utils.py")
@@ -635,6 +773,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ref_extraction":    # own process: defines the octree-side flags, patches .cuda()
         gen_ref_extraction()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_optimization":  # own process: octree-side flags, svox / imageio stand-ins
+        gen_ref_optimization()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "configs":
         gen_configs()

@@ -278,6 +278,47 @@ def test_extraction_sequence_matches_executed_reference(golden_dir):
     assert not ref[rest].any()                                # coarser leaves and internal cells stay empty
 
 
+def test_optimization_loop_matches_executed_reference(golden_dir):
+    """octree/optimization.py `main` was EXECUTED (make_golden.py ref_optimization: the reference's Blender loader,
+    render -> clamp -> MSE -> backward -> torch.optim.SGD per image, validation PSNR per epoch, best-model save) over
+    an svox stand-in whose renderer is this oracle's march wrapped in an autograd Function.  Replaying the run with
+    the oracle pieces the GPU tests use as expected values (`mse_and_grad_out`, `sgd_step`, sequential per-image
+    updates) must give the same PSNR curves and the same saved tree."""
+    z = np.load(os.path.join(golden_dir, "ref_optimization.npz"))
+    H, W, focal, step, lr = int(z["H"]), int(z["W"]), float(z["focal"]), float(z["step_size"]), float(z["lr"])
+    n = z["child"].shape[0]
+    tree = OO.N3Tree(N=2, data_dim=z["data0"].shape[-1], depth_limit=4, init_reserve=n, data_format="SH4")
+    tree.child, tree.parent_depth, tree.n_internal = z["child"].copy(), z["parent_depth"].copy(), n
+    tree.invradius, tree.offset = z["invradius"].astype(np.float32), z["offset"].astype(np.float32)
+    tree.data = z["data0"].astype(np.float32).copy()
+    psnr = lambda mse: -10.0 * np.log(mse) / np.log(10.0)
+
+    def validate():
+        tot = 0.0
+        for c2w, gt in zip(z["val_c2w"], z["val_gt"]):
+            im = OO.volume_render(tree, *OO.persp_rays(c2w, W, H, focal), step_size=step).reshape(H, W, 3)
+            tot += psnr(float(((np.clip(im, 0.0, 1.0) - gt).astype(np.float32) ** 2).mean()))
+        return tot / len(z["val_c2w"])
+    assert abs(validate() - float(z["initial_val_psnr"])) < 2e-4
+    best, best_data = float(z["initial_val_psnr"]), None
+    for ep in range(int(z["epochs"])):
+        tot = 0.0
+        for c2w, gt in zip(z["train_c2w"], z["train_gt"]):
+            rays = OO.persp_rays(c2w, W, H, focal)
+            im = OO.volume_render(tree, *rays, step_size=step)
+            mse, g = OO.mse_and_grad_out(im.reshape(H, W, 3), gt)
+            grad = OO.volume_render_backward(tree, *rays, g.reshape(-1, 3), step_size=step)
+            tree.data = OO.sgd_step(tree.data, grad, lr)
+            tot += psnr(mse)
+        assert abs(tot / len(z["train_c2w"]) - float(z["train_psnr"][ep])) < 2e-4, ep
+        v = validate()
+        assert abs(v - float(z["val_psnr"][ep])) < 2e-4, ep
+        if v > best:
+            best, best_data = v, tree.data.copy()
+    assert z["train_psnr"][-1] > z["train_psnr"][0] + 0.5 and best_data is not None          # it did learn
+    assert np.abs(best_data - z["data_best"]).max() < 2e-5 * np.abs(z["data_best"]).max()
+
+
 @pytest.mark.gpu
 def test_query_and_tree_build_bit_exact():
     import torch
