@@ -44,13 +44,18 @@ def load_ref_module(name, relpath):
 
 
 def _use_reference_octree():
-    """`octree` / `nerf_sh` must resolve to the reference's packages, not to this repo's drop-in shims of the same
-    names: take the repo root off sys.path (the oracle is imported already) and forget the shims."""
-    while ROOT in sys.path:
-        sys.path.remove(ROOT)
+    """`octree` must resolve to the reference's package, not to this repo's drop-in shim of the same name (a regular
+    package beats the reference's namespace package whatever the sys.path order): register a package object whose
+    search path is the reference's directory, and forget any shim modules imported so far."""
+    import types
+    cur = sys.modules.get("octree")
+    if cur is not None and list(getattr(cur, "__path__", [])) == [os.path.join(REF, "octree")]:
+        return
     for name in [m for m in sys.modules if m == "octree" or m.startswith("octree.")]:
-        if not getattr(sys.modules[name], "__file__", None) or not str(sys.modules[name].__file__).startswith(REF):
-            del sys.modules[name]
+        del sys.modules[name]
+    pkg = types.ModuleType("octree")
+    pkg.__path__ = [os.path.join(REF, "octree")]
+    sys.modules["octree"] = pkg
 
 
 def ref_model(sh_deg, flat_c, flat_f):
