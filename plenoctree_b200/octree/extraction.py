@@ -321,8 +321,10 @@ def main(unused_argv):
         if FLAGS.eval:
             from .evaluation import eval_octree
             test = datasets.get_dataset("test", FLAGS, device=dev)
-            psnr, ssim = eval_octree(tree, test, FLAGS)
-            print("Average PSNR", psnr, "SSIM", ssim)
+            from ..nerf.lpips import load_lpips
+            extra = {}
+            psnr, ssim = eval_octree(tree, test, FLAGS, lpips_fn=load_lpips(dev), metrics=extra)
+            print("Average PSNR", psnr, "SSIM", ssim, "LPIPS", extra["lpips"])
     dist_finish()
     return tree
 

@@ -12,7 +12,7 @@ Outputs per task, under <train_dir>/octrees/<octree_name>/: tree.npz (overwritte
     <capacity>
     <raw PSNR> <raw SSIM> <raw LPIPS>
     <optimised PSNR> <SSIM> <LPIPS>          (the raw line again when optimisation left no tree)
-LPIPS is written as nan: it needs the downloaded VGG weights of the `lpips` package, which this build does not have.
+LPIPS is nan unless the evaluation processes find the LPIPS weight files (plenoctree_b200/nerf/lpips.py).
 
 Differences from the reference, on purpose: commands are argv lists (no shell), the metrics are found by pattern
 ("capacity:<used>/<reserved>" in the tree's repr, "Average PSNR <p> SSIM <s>") instead of by counting output lines

@@ -360,6 +360,77 @@ def test_median_cut_and_tree_compression(tmp_path):
     assert "data" in np.load(tmp_path / "raw" / "tree.npz").files
 
 
+def test_lpips_network_and_optional_weights(tmp_path, monkeypatch):
+    """nerf/lpips.py: the VGG-16 feature stack reproduces torchvision's `vgg16().features` at the five LPIPS taps
+    when loaded from its state dict (random weights: the ImageNet file cannot ship), the linear heads load from
+    LPIPS-v0.1-style keys, the distance is 0 for identical images / symmetric / positive, `load_lpips` finds weights in
+    $POB_LPIPS_DIR and returns None without them."""
+    import torchvision
+    from plenoctree_b200.nerf import lpips as L
+    torch.manual_seed(0)
+    tv = torchvision.models.vgg16(weights=None).eval()
+    net = L.LPIPSVGG().eval()
+    net.load_vgg16(tv.state_dict())
+    x = torch.rand(2, 3, 40, 36)
+    taps = net.features(x)
+    for tap, end in zip(taps, (4, 9, 16, 23, 30)):                      # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3
+        with torch.no_grad():
+            want = tv.features[:end](x)
+        assert tap.shape == want.shape and torch.allclose(tap, want, atol=1e-5)
+    heads = {f"lin{l}.model.1.weight": torch.rand(1, c, 1, 1) for l, (_, c) in enumerate(L._BLOCKS)}
+    net.load_linear_heads(heads)
+    a, b = torch.rand(3, 40, 36), torch.rand(3, 40, 36)
+    d_ab, d_ba, d_aa = float(net(a, b)[0]), float(net(b, a)[0]), float(net(a, a)[0])
+    assert d_aa == 0.0 and d_ab > 0 and abs(d_ab - d_ba) < 1e-6 * d_ab
+    assert abs(float(net(2 * a - 1, 2 * b - 1, normalize=False)[0]) - d_ab) < 1e-6 * d_ab
+    # by hand for the first tap: unit-normalised features, squared difference, head weights, spatial mean
+    sa, sb = [(2 * v[None] - 1 - net.shift) / net.scale for v in (a, b)]
+    fa, fb = net.features(sa)[0], net.features(sb)[0]
+    fa, fb = fa / (fa.pow(2).sum(1, keepdim=True).sqrt() + 1e-10), fb / (fb.pow(2).sum(1, keepdim=True).sqrt() + 1e-10)
+    first = float((((fa - fb) ** 2) * heads["lin0.model.1.weight"]).sum(1).mean())
+    zero_rest = {k: (v if k.startswith("lin0") else torch.zeros_like(v)) for k, v in heads.items()}
+    assert abs(float(L.LPIPSVGG().load_vgg16(tv.state_dict()).load_linear_heads(zero_rest)(a, b)[0]) - first) < 1e-6
+    # weight discovery
+    monkeypatch.setenv("POB_LPIPS_DIR", str(tmp_path))
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path / "nohub"))
+    assert L.load_lpips() is None
+    torch.save(tv.state_dict(), tmp_path / "vgg16-397923af.pth")
+    torch.save(heads, tmp_path / "vgg.pth")
+    fn = L.load_lpips()
+    assert fn is not None and abs(fn(a, b) - d_ab) < 1e-6 * d_ab
+
+
+def test_eval_octree_metrics_with_a_stub_renderer(monkeypatch):
+    """octree.evaluation.eval_octree's bookkeeping (PSNR / SSIM averages, optional LPIPS into `metrics`, frames) on the
+    CPU, the renderer replaced by a stub that returns the ground truth plus a known offset."""
+    from plenoctree_b200.octree import evaluation as EV
+
+    class Tree:
+        device = torch.device("cpu")
+
+    class Renderer:
+        def __init__(self, t, step_size):
+            self.calls = 0
+
+        def render_persp(self, c2w, width, height, fx, fast):
+            return torch.full((height, width, 3), 0.5 + 0.1 * float(c2w[0, 0]))
+    monkeypatch.setattr(EV, "VolumeRenderer", Renderer)
+    ds = type("D", (), dict(w=20, h=16, focal=30.0, size=2, camtoworlds=np.stack([np.eye(4), 2 * np.eye(4)]).astype(np.float32),
+                            images=np.full((2, 16, 20, 3), 0.5, np.float32)))
+    args = type("A", (), dict(renderer_step_size=1e-3, no_early_stop=False))
+    psnr, ssim = EV.eval_octree(Tree(), ds, args)
+    want = np.mean([-10 * np.log10(0.1 ** 2), -10 * np.log10(0.2 ** 2)])
+    assert abs(psnr - want) < 1e-4 and 0 < ssim < 1
+    m = {}
+    psnr2, ssim2, frames = EV.eval_octree(Tree(), ds, args, want_frames=True, lpips_fn=lambda gt, im: float((gt - im).abs().mean()),
+                                          metrics=m)
+    assert (psnr2, ssim2) == (psnr, ssim) and len(frames) == 2 and frames[0].dtype == np.uint8
+    assert abs(m["lpips"] - 0.15) < 1e-6
+    m = {}
+    EV.eval_octree(Tree(), ds, args, metrics=m)
+    assert np.isnan(m["lpips"])
+
+
 @pytest.mark.gpu
 def test_cli_chain_train_eval_extract_optimize(tmp_path):
     from oracle import nerf_sh_oracle as O
